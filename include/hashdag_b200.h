@@ -1,0 +1,215 @@
+/*
+ * hashdag_b200.h — C ABI of the B200-native HashDAG engine (libhashdag_b200.so).
+ *
+ * This is the drop-in boundary for the traversal + edit path of AdamYuan/VkHashDAG.  The reference
+ * has no FFI of its own: its seam is C++20 concepts inside one binary.  Each entry
+ * point below names the reference interface it replaces (paths relative to the reference tree).
+ * Templates cannot cross a C ABI, so editors cross as POD descriptors (hd_edit_desc) that select a
+ * compiled-in device predicate.
+ *
+ * Conventions: every call returns an hd_status (0 = OK) and never throws; pointers are plain host
+ * pointers unless the name says "_dev" / the function says "device"; one pool per CUDA device;
+ * calls on one pool are externally serialised, except that hd_trace* may overlap an edit on another
+ * stream (node memory is append-only between GCs, include/hashdag/NodePool.hpp:134-157).
+ */
+#ifndef HASHDAG_B200_H
+#define HASHDAG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HD_NULL_NODE 0xFFFFFFFFu /* include/hashdag/NodePointer.hpp:18 */
+#define HD_MAX_NODE_LEVELS 22u   /* float-mantissa stack: include/hashdag/NodePoolTraversal.hpp:104 */
+#define HD_COLOR_NULL 0xC0000000u /* src/DAGColorPool.hpp:23-34, tag 3 */
+
+typedef enum hd_status {
+	HD_OK = 0,
+	HD_ERR_INVALID = 1,  /* bad argument / config fails Config::Validate (include/hashdag/Config.hpp:48-56) */
+	HD_ERR_CUDA = 2,     /* a CUDA runtime call failed; see hd_last_error() */
+	HD_ERR_OOM = 3,      /* device allocation failed */
+	HD_ERR_OVERFLOW = 4, /* edit scratch (work queues) exhausted; pool unchanged beyond appended garbage */
+	HD_ERR_NO_DEVICE = 5 /* no CUDA device: there is no CPU fallback in the product */
+} hd_status;
+
+/* include/hashdag/Config.hpp:15-57 — pool geometry.  node_levels = bucket_bits_each_level.size(). */
+typedef struct hd_config {
+	uint32_t word_bits_per_page;
+	uint32_t page_bits_per_bucket;
+	uint32_t node_levels;
+	uint32_t bucket_bits_each_level[HD_MAX_NODE_LEVELS];
+} hd_config;
+
+/* include/hashdag/Config.hpp:59-75 — DefaultConfig{}() */
+typedef struct hd_default_config {
+	uint32_t level_count, top_level_count;
+	uint32_t word_bits_per_page, page_bits_per_bucket;
+	uint32_t bucket_bits_per_top_level, bucket_bits_per_bottom_level;
+} hd_default_config;
+
+/* Editors (src/main.cpp:32-150) as POD.  Coordinates are voxel-level integers.
+ *  AABB_FILL    : p0 = aabb_min, p1 = aabb_max (exclusive)         main.cpp:32-70
+ *  SPHERE_FILL  : p0 = center, r2                                  main.cpp:72-150 (EditMode::kFill)
+ *  SPHERE_DIG   : p0 = center, r2                                  (EditMode::kDig)
+ *  TERRAIN_FILL : integer value-noise height field (synthetic scene generator):
+ *                 aux = seed, p0 = {base_height, first_cell_bits, octaves}, p1 = {first_amplitude,0,0};
+ *                 octave o has lattice cell 2^(first_cell_bits-2o) voxels and amplitude first_amplitude>>(2o);
+ *                 voxel (x,y,z) becomes solid iff y < height(x,z).
+ */
+typedef enum hd_edit_kind {
+	HD_EDIT_AABB_FILL = 0,
+	HD_EDIT_SPHERE_FILL = 1,
+	HD_EDIT_SPHERE_DIG = 2,
+	HD_EDIT_TERRAIN_FILL = 3
+} hd_edit_kind;
+
+typedef struct hd_edit_desc {
+	uint32_t kind;
+	uint32_t p0[3];
+	uint32_t p1[3];
+	uint32_t aux;
+	uint64_t r2;
+} hd_edit_desc;
+
+/* Counters of one hd_edit_batch call (all monotone sums over the batch). */
+typedef struct hd_edit_stats {
+	uint64_t visited_nodes;   /* inner work items expanded (edit_node calls, NodePool.hpp:362) */
+	uint64_t visited_leaves;  /* leaf work items (edit_leaf calls, NodePool.hpp:319) */
+	uint64_t upserts;         /* upsert_node calls issued (NodePool.hpp:159) */
+	uint64_t appended_nodes;  /* nodes that missed and were appended */
+	uint64_t appended_words;  /* words appended including page padding */
+	uint64_t overflow_count;  /* full buckets hit (NodePool.hpp:137-139,195): >0 voids parity */
+	uint64_t in_range_voxels; /* reserved (computed by callers analytically) */
+	uint64_t scan_words;      /* bucket words the GPU lookup actually read */
+} hd_edit_stats;
+
+/* src/rg/TracePass.cpp:10-18 tracer_pass::PC_Data == shader/src/trace.frag:15-23 push constants (84 B). */
+typedef struct hd_trace_params {
+	float pos[3], look[3], side[3], up[3];
+	uint32_t width, height;
+	uint32_t voxel_level;
+	uint32_t dag_root, dag_leaf_level;
+	uint32_t color_root, color_leaf_level;
+	float proj_factor;
+	uint32_t type; /* 0 diffuse*colour, 1 normal, 2 iteration heat (trace.frag:395-401) */
+} hd_trace_params;
+
+/* Per-pixel parity record (16 B): vox_pos (trace.frag:240-246) and
+ * packed = hit<<31 | log2(vox_size)<<24 | fetched colour as RGB8 (r in bits 0..7), 0 when !hit. */
+typedef struct hd_hit_record {
+	uint32_t vox[3];
+	uint32_t packed;
+} hd_hit_record;
+
+/* Output planes of a trace call; any pointer may be NULL to skip that plane. */
+typedef struct hd_trace_outputs {
+	uint32_t *rgba8;       /* shaded frame, trace.frag:395-401 converted to UNORM8 (r low byte, a = 255) */
+	hd_hit_record *hits;   /* parity records */
+	uint32_t *iters;       /* loop iterations, trace.frag:129 */
+} hd_trace_outputs;
+
+/* Screen-tile sharding of one frame over `world` GPUs: tile t = ty*tiles_x+tx (tile_w x tile_h px)
+ * belongs to rank t % world; a rank's outputs are tile-major: index = (t/world)*tile_w*tile_h + ly*tile_w + lx. */
+typedef struct hd_tile_shard {
+	uint32_t tile_w, tile_h;
+	uint32_t rank, world;
+} hd_tile_shard;
+
+/* One contiguous run of words changed since the last hd_dirty_reset — the analogue of
+ * DAGNodePool::m_page_write_ranges (src/DAGNodePool.hpp:44-46,62-69). */
+typedef struct hd_dirty_range {
+	uint32_t word_offset;
+	uint32_t word_count;
+} hd_dirty_range;
+
+typedef struct hd_pool hd_pool;
+
+/* ---- library ---- */
+const char *hd_version(void);
+const char *hd_last_error(void);
+int hd_device_count(void);
+
+/* ---- config helpers: include/hashdag/Config.hpp ---- */
+hd_status hd_config_from_default(const hd_default_config *dc, hd_config *out); /* Config.hpp:66-74 */
+int hd_config_validate(const hd_config *cfg);                                  /* Config.hpp:48-56 */
+uint32_t hd_config_total_buckets(const hd_config *cfg);                        /* Config.hpp:39-44 */
+uint64_t hd_config_total_words(const hd_config *cfg);                          /* Config.hpp:46 */
+uint32_t hd_config_level_base_bucket(const hd_config *cfg, uint32_t level);    /* Config.hpp:33-38 */
+
+/* ---- pool: replaces DAGNodePool::Create / ctor (src/DAGNodePool.hpp:84-92, DAGNodePool.cpp:9-47) ---- */
+hd_status hd_pool_create(const hd_config *cfg, int device, hd_pool **out);
+void hd_pool_destroy(hd_pool *pool);
+hd_status hd_pool_get_config(const hd_pool *pool, hd_config *out); /* NodePoolBase::GetConfig, NodePool.hpp:404 */
+hd_status hd_pool_clear(hd_pool *pool);                            /* forget all nodes (fresh pool) */
+/* root bookkeeping: DAGNodePool::SetRoot/GetRoot (src/DAGNodePool.hpp:96-97) */
+hd_status hd_pool_set_root(hd_pool *pool, uint32_t root);
+uint32_t hd_pool_get_root(const hd_pool *pool);
+/* raw device pointers (for NCCL / torch interop); words = flat uint32 address space */
+void *hd_pool_words_dev(hd_pool *pool);
+void *hd_pool_bucket_words_dev(hd_pool *pool);
+void *hd_pool_stream(hd_pool *pool); /* cudaStream_t all pool work is enqueued on */
+
+/* host <-> device mirror interop: the ReadPage/WritePage callbacks (src/DAGNodePool.hpp:58-69) and
+ * DAGNodePool::Flush (src/DAGNodePool.cpp:56-85). */
+hd_status hd_pool_upload_words(hd_pool *pool, uint32_t word_offset, const uint32_t *src, uint32_t count);
+hd_status hd_pool_read_words(hd_pool *pool, uint32_t word_offset, uint32_t *dst, uint32_t count);
+hd_status hd_pool_upload_bucket_words(hd_pool *pool, uint32_t first_bucket, const uint32_t *src, uint32_t count);
+hd_status hd_pool_read_bucket_words(hd_pool *pool, uint32_t first_bucket, uint32_t *dst, uint32_t count);
+/* m_filled_node_pointers (NodePool.hpp:54,240-262); made on first use like make_filled_node_pointers() */
+hd_status hd_pool_filled_nodes(hd_pool *pool, uint32_t *out_ptrs /* [node_levels] */);
+
+/* ---- edit: replaces NodePoolBase::Edit (NodePool.hpp:405-417) and
+ *      NodePoolThreadedEdit::ThreadedEdit (NodePoolThreadedEdit.hpp:104-126) ----
+ * Applies edits[0..n) in index order (same final voxel set, hence the same canonical DAG, as n sequential
+ * reference Edit calls) in ONE level-synchronous GPU pass.  stats may be NULL. */
+hd_status hd_edit_batch(hd_pool *pool, uint32_t root_in, const hd_edit_desc *edits, uint32_t n,
+                        uint32_t *root_out, hd_edit_stats *stats);
+/* find-or-insert of explicit nodes: upsert_inner_node / upsert_leaf (NodePool.hpp:228-238), used by tests.
+ * nodes = n packed nodes, each `words_each` words (2 for a leaf level). out_ptrs[n]. */
+hd_status hd_upsert_nodes(hd_pool *pool, uint32_t level, const uint32_t *nodes, uint32_t words_each, uint32_t n,
+                          uint32_t *out_ptrs);
+
+/* ---- colour pool: the DAGColorPool buffers the tracer reads (src/DAGColorPool.hpp:43-52; bindings 1,2 of
+ *      shader/src/trace.frag:6-7).  Mutation on the GPU is a "next" row. ---- */
+hd_status hd_color_upload(hd_pool *pool, const uint32_t *color_nodes, uint64_t node_words, const uint32_t *color_leaves,
+                          uint64_t leaf_words);
+
+/* ---- trace: replaces TracePass::CmdExecute + shader/src/trace.frag main() (TracePass.cpp:106-139) ----
+ * Outputs are HOST pointers (copied back inside the call) for hd_trace / hd_trace_tiles and DEVICE pointers for
+ * the *_dev variants, which only enqueue on hd_pool_stream() and do not synchronise. */
+hd_status hd_trace(hd_pool *pool, const hd_trace_params *params, const hd_trace_outputs *host_out);
+hd_status hd_trace_dev(hd_pool *pool, const hd_trace_params *params, const hd_trace_outputs *dev_out);
+hd_status hd_trace_tiles(hd_pool *pool, const hd_trace_params *params, const hd_tile_shard *shard,
+                         const hd_trace_outputs *host_out);
+hd_status hd_trace_tiles_dev(hd_pool *pool, const hd_trace_params *params, const hd_tile_shard *shard,
+                             const hd_trace_outputs *dev_out);
+/* pixels a rank owns under a shard (size of its output planes) */
+uint64_t hd_tile_shard_pixels(const hd_trace_params *params, const hd_tile_shard *shard);
+/* single pick ray: NodePoolTraversal::Traversal<float> (NodePoolTraversal.hpp:93-256), main.cpp:320-321.
+ * Returns hit flag in *out_hit and the float hit position in out_pos[3]. */
+hd_status hd_traverse_ray(hd_pool *pool, uint32_t root, const float o[3], const float d[3], int *out_hit,
+                          float out_pos[3]);
+
+/* ---- replica sync: replaces DAGNodePool::Flush for the multi-GPU case ----
+ * After an edit the editing rank packs every dirty range into one staging buffer
+ *   [u32 n_ranges][u32 payload_words][u32 root][u32 reserved] [hd_dirty_range x n] [payload words]
+ *   followed by [u32 n_bucket_updates] [(bucket, words) x n]
+ * which the caller broadcasts (one NCCL broadcast over NVLink) and replicas apply with a scatter kernel. */
+hd_status hd_dirty_count(hd_pool *pool, uint32_t *n_ranges, uint64_t *packed_bytes);
+hd_status hd_dirty_ranges(hd_pool *pool, hd_dirty_range *out, uint32_t capacity, uint32_t *n_out);
+hd_status hd_dirty_pack_dev(hd_pool *pool, void *staging_dev, uint64_t capacity_bytes, uint64_t *packed_bytes);
+hd_status hd_dirty_apply_dev(hd_pool *pool, const void *staging_dev, uint64_t packed_bytes);
+hd_status hd_dirty_reset(hd_pool *pool);
+
+/* ---- introspection used by tests / benches ---- */
+hd_status hd_pool_used_words(hd_pool *pool, uint64_t *out); /* sum of bucket_words */
+hd_status hd_sync(hd_pool *pool);
+uint64_t hd_kernel_launches(void); /* kernels this library has launched so far (bench gpu_launches) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HASHDAG_B200_H */
