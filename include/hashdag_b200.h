@@ -194,10 +194,11 @@ hd_status hd_traverse_ray(hd_pool *pool, uint32_t root, const float o[3], const 
                           float out_pos[3]);
 
 /* ---- replica sync: replaces DAGNodePool::Flush for the multi-GPU case ----
- * After an edit the editing rank packs every dirty range into one staging buffer
- *   [u32 n_ranges][u32 payload_words][u32 root][u32 reserved] [hd_dirty_range x n] [payload words]
- *   followed by [u32 n_bucket_updates] [(bucket, words) x n]
- * which the caller broadcasts (one NCCL broadcast over NVLink) and replicas apply with a scatter kernel. */
+ * Buckets are append-only, so the dirty set is [words at last sync, bucket_words) of every bucket.  The editing
+ * rank packs it into one staging buffer (u32 words)
+ *   [n_ranges][payload_words][root][0]  n_ranges x {word_offset, word_count, payload_offset}  payload...
+ * which the caller broadcasts (one NCCL broadcast over NVLink); replicas apply it with a scatter kernel that also
+ * advances their bucket_words, and publish the root last. */
 hd_status hd_dirty_count(hd_pool *pool, uint32_t *n_ranges, uint64_t *packed_bytes);
 hd_status hd_dirty_ranges(hd_pool *pool, hd_dirty_range *out, uint32_t capacity, uint32_t *n_out);
 hd_status hd_dirty_pack_dev(hd_pool *pool, void *staging_dev, uint64_t capacity_bytes, uint64_t *packed_bytes);

@@ -1021,6 +1021,51 @@ uint64_t orc_trace_frame(const uint32_t *nodes, const uint32_t *color_nodes, con
 	return total.load();
 }
 
+// Primary rays of a frame through the HOST tracer (Traversal<float>: no LOD, no colour), rays generated as
+// trace.frag:366-377.  Mirror of ref_trace_frame_host in oracle/ref_harness.cpp; pins ray generation + traversal.
+uint64_t orc_trace_frame_host(const uint32_t *nodes, uint32_t node_levels, const hd_trace_params *P, uint32_t row_begin,
+                              uint32_t row_end, uint32_t row_step, uint32_t n_threads, uint8_t *hit, float *pos) {
+	std::atomic<uint64_t> hits{0};
+	if (!n_threads)
+		n_threads = 1;
+	if (!row_step)
+		row_step = 1;
+	auto work = [&](uint32_t tid) {
+		uint64_t h = 0;
+		uint32_t k = 0;
+		for (uint32_t y = row_begin; y < row_end; y += row_step, ++k) {
+			if (k % n_threads != tid)
+				continue;
+			for (uint32_t x = 0; x < P->width; ++x) {
+				float cx = (float(x) + 0.5f) / float(P->width), cy = (float(y) + 0.5f) / float(P->height);
+				cx = cx * 2.0f - 1.0f, cy = cy * 2.0f - 1.0f;
+				float d[3], out[3];
+				for (int i = 0; i < 3; ++i)
+					d[i] = (P->look[i] - P->side[i] * cx) - P->up[i] * cy;
+				normalize3(d);
+				int r = orc_traverse(nodes, node_levels, P->dag_root, P->pos, d, out);
+				size_t at = size_t(y) * P->width + x;
+				if (hit)
+					hit[at] = uint8_t(r);
+				if (pos && r)
+					pos[at * 3] = out[0], pos[at * 3 + 1] = out[1], pos[at * 3 + 2] = out[2];
+				h += uint64_t(r);
+			}
+		}
+		hits += h;
+	};
+	if (n_threads == 1)
+		work(0);
+	else {
+		std::vector<std::thread> th;
+		for (uint32_t t = 0; t < n_threads; ++t)
+			th.emplace_back(work, t);
+		for (auto &t : th)
+			t.join();
+	}
+	return hits.load();
+}
+
 // Colour lookup alone (checked against the reference's VBR iterator in oracle/_ref).  out = RGB floats.
 void orc_color_fetch(const uint32_t *color_nodes, const uint32_t *color_leaves, uint32_t root, uint32_t voxel_level,
                      uint32_t leaf_level, uint32_t x, uint32_t y, uint32_t z, float out[3]) {

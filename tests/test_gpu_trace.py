@@ -1,0 +1,113 @@
+"""GPU parity of kernel #1 (trace) against the CPU oracle, through the C ABI with host buffers."""
+import numpy as np
+import pytest
+
+from vkhashdag_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+NULL = abi.NULL
+
+
+def build_scene(oracle, level_count=10, edits=None):
+    cfg = abi.default_config(level_count=level_count, top_level_count=9)
+    pool = oracle.pool(cfg)
+    res = 1 << cfg.voxel_level
+    if edits is None:
+        edits = [abi.sphere((res // 2,) * 3, (res // 3) ** 2)]
+    root = pool.edit_batch(NULL, edits)
+    return cfg, pool, root
+
+
+def compare_frames(oracle, hd, cfg, opool, root, cams, W, H, color=None, types=(0,)):
+    dev = hd.DAGNodePool(cfg)
+    dev.UploadFrom(opool)
+    color_root, cn, cl, cleaf = abi.COLOR_NULL, None, None, 10
+    if color is not None:
+        color_root, cn, cl, cleaf = color
+        dev.UploadColor(cn, cl)
+    for (pos, yaw, pitch, lod) in cams:
+        for t in types:
+            P = abi.camera_params(cfg, root, pos, yaw, pitch, W, H, color_root=color_root, color_leaf_level=cleaf,
+                                  type_=t, lod=lod)
+            exp = oracle.trace_frame(opool.words_ptr, P, cn, cl)
+            got = dev.Trace(P)
+            assert np.array_equal(got["iters"], exp["iters"]), f"iters differ cam={pos, yaw, pitch, lod}"
+            assert np.array_equal(got["hits"], exp["hits"]), f"hit records differ cam={pos, yaw, pitch, lod}"
+            assert np.array_equal(got["rgba8"], exp["rgba8"]), f"frame differs cam={pos, yaw, pitch, lod} type={t}"
+    dev.close()
+    return exp
+
+
+def test_trace_sphere_cfg1(oracle, hd):
+    """BASELINE config 1: 2^10 sphere, 1280x720, camera (0.5,0.5,1.5) looking -z."""
+    cfg, opool, root = build_scene(oracle)
+    exp = compare_frames(oracle, hd, cfg, opool, root, [((0.5, 0.5, 1.5), np.pi, 0.0, True)], 1280, 720, types=(0, 1, 2))
+    assert (exp["hits"]["packed"] >> 31).sum() > 10000
+
+
+def test_trace_cameras_lod_and_full_detail(oracle, hd):
+    res = 1 << 10
+    edits = [abi.sphere((512, 512, 512), 341 ** 2), abi.sphere((512, 512, 300), 150 ** 2, dig=True),
+             abi.sphere((700, 600, 512), 200 ** 2), abi.aabb((100, 50, 100), (400, 90, 900))]
+    cfg, opool, root = build_scene(oracle, edits=edits)
+    cams = [((0.5, 0.5, 1.5), np.pi, 0.0, False), ((0.1, 0.9, 0.1), 0.7, -0.6, True), ((0.5, 0.5, 0.5), 2.0, 0.3, True),
+            ((-0.2, 0.3, 0.4), 1.4, 0.1, False), ((0.52, 0.97, 0.51), 0.0, -1.5, True)]
+    compare_frames(oracle, hd, cfg, opool, root, cams, 320, 200)
+
+
+def test_trace_odd_sizes_and_empty(oracle, hd):
+    cfg, opool, root = build_scene(oracle, level_count=8)
+    compare_frames(oracle, hd, cfg, opool, root, [((0.5, 0.5, 1.4), np.pi, 0.0, True)], 333, 77)
+    compare_frames(oracle, hd, cfg, opool, NULL, [((0.5, 0.5, 1.4), np.pi, 0.0, True)], 64, 32)
+    compare_frames(oracle, hd, cfg, opool, root, [((0.5, 0.5, 1.4), np.pi, 0.0, True)], 1, 1)
+
+
+def test_trace_tile_shards_cover_frame(oracle, hd):
+    cfg, opool, root = build_scene(oracle, level_count=9)
+    dev = hd.DAGNodePool(cfg)
+    dev.UploadFrom(opool)
+    W, H, tw, th = 400, 250, 64, 64
+    P = abi.camera_params(cfg, root, (0.5, 0.6, 1.3), np.pi, -0.2, W, H)
+    full = dev.Trace(P)
+    tiles_x, tiles_y = -(-W // tw), -(-H // th)
+    for world in (1, 2, 3, 8):
+        seen = np.zeros((H, W), bool)
+        for rank in range(world):
+            part = dev.Trace(P, shard=(tw, th, rank, world))
+            n_local = len(range(rank, tiles_x * tiles_y, world))
+            assert part["rgba8"].size == n_local * tw * th
+            for lt in range(n_local):
+                t = lt * world + rank
+                tx, ty = t % tiles_x, t // tiles_x
+                x0, y0 = tx * tw, ty * th
+                w, h = min(tw, W - x0), min(th, H - y0)
+                for name in ("rgba8", "iters"):
+                    blk = part[name][lt * tw * th:(lt + 1) * tw * th].reshape(th, tw)[:h, :w]
+                    assert np.array_equal(blk, full[name][y0:y0 + h, x0:x0 + w])
+                blk = part["hits"][lt * tw * th:(lt + 1) * tw * th].reshape(th, tw)[:h, :w]
+                assert np.array_equal(blk, full["hits"][y0:y0 + h, x0:x0 + w])
+                seen[y0:y0 + h, x0:x0 + w] = True
+        assert seen.all()
+    dev.close()
+
+
+def test_pick_ray_matches_host_traversal(oracle, hd):
+    cfg, opool, root = build_scene(oracle)
+    dev = hd.DAGNodePool(cfg)
+    dev.UploadFrom(opool)
+    rng = np.random.default_rng(7)
+    rays = [((0.5, 0.5, 1.5), (0, 0, -1)), ((0.5, 0.5, 1.5), (0.1, -0.2, -1)), ((-0.2, 0.3, 0.4), (1, 0.3, 0.2)),
+            ((0.5, 0.5, 1.5), (0.6, 0, -1))]
+    for _ in range(60):
+        rays.append((tuple(rng.uniform(-0.5, 1.5, 3)), tuple(rng.normal(size=3))))
+    for o, d in rays:
+        d = np.array(d, np.float32)
+        d = d / np.float32(np.sqrt(np.float32(np.dot(d, d))))
+        exp = oracle.traverse(opool.words_ptr, cfg.node_levels, root, o, d)
+        got = dev.Traversal(root, o, d)
+        assert (exp is None) == (got is None)
+        if exp is not None:
+            assert np.array_equal(exp.view(np.uint32), got.view(np.uint32))
+    assert dev.Traversal(NULL, (0.5, 0.5, 1.5), (0, 0, -1)) is None
+    dev.close()

@@ -1,0 +1,164 @@
+"""vkhashdag_b200/abi.py — ctypes mirror of include/hashdag_b200.h plus the host-side helpers that build its PODs.
+
+Mirrors, on the Python side, the reference's host types for this path:
+  HdConfig / default_config   include/hashdag/Config.hpp:15-75
+  aabb / sphere / terrain     editor structs of src/main.cpp:32-150 as hd_edit_desc
+  camera_params               src/Camera.hpp:36-52 + src/rg/TracePass.cpp:106-134 (push-constant block)
+"""
+import ctypes as C
+
+import numpy as np
+
+MAX_LEVELS = 22
+NULL = 0xFFFFFFFF
+COLOR_NULL = 0xC0000000
+
+EDIT_AABB_FILL, EDIT_SPHERE_FILL, EDIT_SPHERE_DIG, EDIT_TERRAIN_FILL = 0, 1, 2, 3
+
+
+class HdConfig(C.Structure):
+    _fields_ = [("word_bits_per_page", C.c_uint32), ("page_bits_per_bucket", C.c_uint32),
+                ("node_levels", C.c_uint32), ("bucket_bits_each_level", C.c_uint32 * MAX_LEVELS)]
+
+    def bucket_bits(self):
+        return [self.bucket_bits_each_level[i] for i in range(self.node_levels)]
+
+    @property
+    def voxel_level(self):
+        return self.node_levels + 1
+
+    def total_buckets(self):
+        return sum(1 << b for b in self.bucket_bits())
+
+    def total_words(self):
+        return self.total_buckets() << (self.word_bits_per_page + self.page_bits_per_bucket)
+
+    def level_bases(self):
+        out, acc = [], 0
+        for b in self.bucket_bits():
+            out.append(acc)
+            acc += 1 << b
+        return out
+
+
+class HdDefaultConfig(C.Structure):
+    _fields_ = [("level_count", C.c_uint32), ("top_level_count", C.c_uint32), ("word_bits_per_page", C.c_uint32),
+                ("page_bits_per_bucket", C.c_uint32), ("bucket_bits_per_top_level", C.c_uint32),
+                ("bucket_bits_per_bottom_level", C.c_uint32)]
+
+
+class HdEditDesc(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("p0", C.c_uint32 * 3), ("p1", C.c_uint32 * 3), ("aux", C.c_uint32),
+                ("r2", C.c_uint64)]
+
+
+class HdTraceParams(C.Structure):
+    _fields_ = [("pos", C.c_float * 3), ("look", C.c_float * 3), ("side", C.c_float * 3), ("up", C.c_float * 3),
+                ("width", C.c_uint32), ("height", C.c_uint32), ("voxel_level", C.c_uint32), ("dag_root", C.c_uint32),
+                ("dag_leaf_level", C.c_uint32), ("color_root", C.c_uint32), ("color_leaf_level", C.c_uint32),
+                ("proj_factor", C.c_float), ("type", C.c_uint32)]
+
+
+assert C.sizeof(HdTraceParams) == 84 and C.sizeof(HdEditDesc) == 40
+
+HIT_DTYPE = np.dtype([("vox", np.uint32, 3), ("packed", np.uint32)])
+
+
+def default_config(level_count=17, top_level_count=9, word_bits_per_page=9, page_bits_per_bucket=2,
+                   bucket_bits_per_top_level=10, bucket_bits_per_bottom_level=16):
+    """include/hashdag/Config.hpp:59-75 DefaultConfig{}() in pure Python."""
+    cfg = HdConfig()
+    cfg.word_bits_per_page, cfg.page_bits_per_bucket = word_bits_per_page, page_bits_per_bucket
+    cfg.node_levels = level_count - 1
+    for l in range(level_count - 1):
+        cfg.bucket_bits_each_level[l] = bucket_bits_per_top_level if l < top_level_count else bucket_bits_per_bottom_level
+    return cfg
+
+
+def aabb(lo, hi):
+    d = HdEditDesc()
+    d.kind = EDIT_AABB_FILL
+    d.p0[:] = lo
+    d.p1[:] = hi
+    return d
+
+
+def sphere(center, r2, dig=False):
+    d = HdEditDesc()
+    d.kind = EDIT_SPHERE_DIG if dig else EDIT_SPHERE_FILL
+    d.p0[:] = center
+    d.r2 = int(r2)
+    return d
+
+
+def terrain(voxel_level, seed=0x5EED, octaves=4):
+    """The synthetic noise terrain of SURVEY §8d cfg2 scaled to the resolution (oracle/terrain.h)."""
+    res = 1 << voxel_level
+    d = HdEditDesc()
+    d.kind = EDIT_TERRAIN_FILL
+    d.aux = seed
+    d.p0[:] = (res // 4, voxel_level - 2, octaves)
+    d.p1[:] = (res // 4, 0, 0)
+    return d
+
+
+def edit_array(edits):
+    arr = (HdEditDesc * len(edits))()
+    for i, e in enumerate(edits):
+        arr[i] = e
+    return arr
+
+
+def random_spheres(n, voxel_level, seed=1234, rmin=16, rmax=256, y_lo=None, y_hi=None):
+    """xorshift32 centres in the terrain band, radius uniform, alternating fill/dig."""
+    res = 1 << voxel_level
+    y_lo = res // 4 if y_lo is None else y_lo
+    y_hi = res // 4 + res // 3 if y_hi is None else y_hi
+    s = seed & 0xFFFFFFFF
+
+    def nxt():
+        nonlocal s
+        s ^= (s << 13) & 0xFFFFFFFF
+        s ^= s >> 17
+        s ^= (s << 5) & 0xFFFFFFFF
+        return s
+
+    out = []
+    for i in range(n):
+        x, z = nxt() % res, nxt() % res
+        y = y_lo + nxt() % max(1, y_hi - y_lo)
+        r = rmin + nxt() % (rmax - rmin + 1)
+        out.append(sphere((x, y, z), r * r, dig=bool(i & 1)))
+    return out
+
+
+def camera_params(cfg, root, pos, yaw, pitch, width, height, fov=np.pi / 3, color_root=COLOR_NULL,
+                  color_leaf_level=10, type_=0, lod=True):
+    """Push-constant block as src/rg/TracePass.cpp:106-134 + src/Camera.hpp:36-52 build it (float32 host maths)."""
+    f = np.float32
+    cy, sy, cp, sp = f(np.cos(f(yaw))), f(np.sin(f(yaw))), f(np.cos(f(pitch))), f(np.sin(f(pitch)))
+    # trans = rotate(yaw, +Y) * rotate(pitch, -X); look = trans*(0,0,1); side = trans*(1,0,0)
+    look = np.array([sy * cp, sp, cy * cp], dtype=f)
+    side = np.array([cy, 0, -sy], dtype=f)
+    look = look / f(np.sqrt(f(np.dot(look, look))))
+    tg = f(np.tan(f(fov) * f(0.5)))
+    aspect = f(width) / f(height)
+    side = side / f(np.sqrt(f(np.dot(side, side)))) * tg * aspect
+    up = np.cross(look, side).astype(f)
+    up = up / f(np.sqrt(f(np.dot(up, up)))) * tg
+    P = HdTraceParams()
+    P.pos[:] = [float(v) for v in pos]
+    P.look[:] = [float(v) for v in look]
+    P.side[:] = [float(v) for v in side]
+    P.up[:] = [float(v) for v in up]
+    P.width, P.height = width, height
+    P.voxel_level = cfg.node_levels + 1
+    P.dag_root = root
+    P.dag_leaf_level = cfg.node_levels
+    P.color_root, P.color_leaf_level = color_root, color_leaf_level
+    inv_2tan = f(1.0) / (f(2.0) * f(np.tan(f(0.5) * f(fov))))
+    P.proj_factor = float(inv_2tan / (f(1.0) / f(height))) if lod else float("inf")
+    P.type = type_
+    return P
+
+

@@ -1,0 +1,351 @@
+"""vkhashdag_b200/api.py — host-side mirror of the reference's pool interface over the C ABI (ctypes).
+
+Names follow the reference so parity tests read like its own tests:
+  DAGNodePool.Create / Edit / ThreadedEdit / Traversal / GetConfig / SetRoot / GetRoot / Flush
+      (src/DAGNodePool.hpp:84-99, include/hashdag/NodePool.hpp:404-417, NodePoolThreadedEdit.hpp:104-126,
+       NodePoolTraversal.hpp:93-256)
+  AABBEditor / SphereEditor / TerrainEditor      editor structs (src/main.cpp:32-150) as POD descriptors
+
+There is NO CPU fallback: importing works without a GPU (so the library can be inspected), every compute call
+raises HashDagError(HD_ERR_NO_DEVICE) when no CUDA device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .abi import (COLOR_NULL, HIT_DTYPE, NULL, HdConfig, HdDefaultConfig, HdEditDesc, HdTraceParams, edit_array)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libhashdag_b200.so")
+
+HD_OK, HD_ERR_INVALID, HD_ERR_CUDA, HD_ERR_OOM, HD_ERR_OVERFLOW, HD_ERR_NO_DEVICE = range(6)
+
+
+class HdEditStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("visited_nodes", "visited_leaves", "upserts", "appended_nodes",
+                                          "appended_words", "overflow_count", "in_range_voxels", "scan_words")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class HdTraceOutputs(C.Structure):
+    _fields_ = [("rgba8", C.c_void_p), ("hits", C.c_void_p), ("iters", C.c_void_p)]
+
+
+class HdTileShard(C.Structure):
+    _fields_ = [("tile_w", C.c_uint32), ("tile_h", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32)]
+
+
+class HdDirtyRange(C.Structure):
+    _fields_ = [("word_offset", C.c_uint32), ("word_count", C.c_uint32)]
+
+
+class HashDagError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"hd_status {status}: {msg}")
+        self.status = status
+
+
+_lib = None
+
+# every symbol include/hashdag_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "hd_version", "hd_last_error", "hd_device_count", "hd_config_from_default", "hd_config_validate",
+    "hd_config_total_buckets", "hd_config_total_words", "hd_config_level_base_bucket", "hd_pool_create",
+    "hd_pool_destroy", "hd_pool_get_config", "hd_pool_clear", "hd_pool_set_root", "hd_pool_get_root",
+    "hd_pool_words_dev", "hd_pool_bucket_words_dev", "hd_pool_stream", "hd_pool_upload_words", "hd_pool_read_words",
+    "hd_pool_upload_bucket_words", "hd_pool_read_bucket_words", "hd_pool_filled_nodes", "hd_edit_batch",
+    "hd_upsert_nodes", "hd_color_upload", "hd_trace", "hd_trace_dev", "hd_trace_tiles", "hd_trace_tiles_dev",
+    "hd_tile_shard_pixels", "hd_traverse_ray", "hd_dirty_count", "hd_dirty_ranges", "hd_dirty_pack_dev",
+    "hd_dirty_apply_dev", "hd_dirty_reset", "hd_pool_used_words", "hd_sync", "hd_kernel_launches",
+]
+
+
+def lib():
+    """Load libhashdag_b200.so (built in-tree by vkhashdag_b200/build.py).  Fails loudly when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} is missing: run `python -m vkhashdag_b200.build` (there is no fallback)")
+    L = C.CDLL(LIB_PATH)
+    u32, u64, vp, ci = C.c_uint32, C.c_uint64, C.c_void_p, C.c_int
+    pu32 = C.POINTER(C.c_uint32)
+    L.hd_version.restype = C.c_char_p
+    L.hd_last_error.restype = C.c_char_p
+    L.hd_device_count.restype = ci
+    L.hd_config_from_default.argtypes = [C.POINTER(HdDefaultConfig), C.POINTER(HdConfig)]
+    L.hd_config_validate.argtypes = [C.POINTER(HdConfig)]
+    L.hd_config_total_buckets.restype = u32
+    L.hd_config_total_buckets.argtypes = [C.POINTER(HdConfig)]
+    L.hd_config_total_words.restype = u64
+    L.hd_config_total_words.argtypes = [C.POINTER(HdConfig)]
+    L.hd_config_level_base_bucket.restype = u32
+    L.hd_config_level_base_bucket.argtypes = [C.POINTER(HdConfig), u32]
+    L.hd_pool_create.argtypes = [C.POINTER(HdConfig), ci, C.POINTER(vp)]
+    L.hd_pool_destroy.argtypes = [vp]
+    L.hd_pool_destroy.restype = None
+    L.hd_pool_get_config.argtypes = [vp, C.POINTER(HdConfig)]
+    L.hd_pool_clear.argtypes = [vp]
+    L.hd_pool_set_root.argtypes = [vp, u32]
+    L.hd_pool_get_root.restype = u32
+    L.hd_pool_get_root.argtypes = [vp]
+    for f in ("hd_pool_words_dev", "hd_pool_bucket_words_dev", "hd_pool_stream"):
+        getattr(L, f).restype = vp
+        getattr(L, f).argtypes = [vp]
+    L.hd_pool_upload_words.argtypes = [vp, u32, vp, u32]
+    L.hd_pool_read_words.argtypes = [vp, u32, vp, u32]
+    L.hd_pool_upload_bucket_words.argtypes = [vp, u32, vp, u32]
+    L.hd_pool_read_bucket_words.argtypes = [vp, u32, vp, u32]
+    L.hd_pool_filled_nodes.argtypes = [vp, pu32]
+    L.hd_edit_batch.argtypes = [vp, u32, C.POINTER(HdEditDesc), u32, pu32, C.POINTER(HdEditStats)]
+    L.hd_upsert_nodes.argtypes = [vp, u32, vp, u32, u32, vp]
+    L.hd_color_upload.argtypes = [vp, vp, u64, vp, u64]
+    L.hd_trace.argtypes = [vp, C.POINTER(HdTraceParams), C.POINTER(HdTraceOutputs)]
+    L.hd_trace_dev.argtypes = [vp, C.POINTER(HdTraceParams), C.POINTER(HdTraceOutputs)]
+    L.hd_trace_tiles.argtypes = [vp, C.POINTER(HdTraceParams), C.POINTER(HdTileShard), C.POINTER(HdTraceOutputs)]
+    L.hd_trace_tiles_dev.argtypes = [vp, C.POINTER(HdTraceParams), C.POINTER(HdTileShard), C.POINTER(HdTraceOutputs)]
+    L.hd_tile_shard_pixels.restype = u64
+    L.hd_tile_shard_pixels.argtypes = [C.POINTER(HdTraceParams), C.POINTER(HdTileShard)]
+    L.hd_traverse_ray.argtypes = [vp, u32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(ci),
+                                  C.POINTER(C.c_float)]
+    L.hd_dirty_count.argtypes = [vp, pu32, C.POINTER(u64)]
+    L.hd_dirty_ranges.argtypes = [vp, C.POINTER(HdDirtyRange), u32, pu32]
+    L.hd_dirty_pack_dev.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.hd_dirty_apply_dev.argtypes = [vp, vp, u64]
+    L.hd_dirty_reset.argtypes = [vp]
+    L.hd_pool_used_words.argtypes = [vp, C.POINTER(u64)]
+    L.hd_sync.argtypes = [vp]
+    L.hd_kernel_launches.restype = u64
+    _lib = L
+    return L
+
+
+def _check(status):
+    if status != HD_OK:
+        raise HashDagError(status, lib().hd_last_error().decode(errors="replace"))
+
+
+def kernel_launches():
+    return int(lib().hd_kernel_launches())
+
+
+# ---- editors (src/main.cpp:32-150) -----------------------------------------------------------------
+class AABBEditor:
+    def __init__(self, aabb_min, aabb_max):
+        self.desc = abi.aabb(aabb_min, aabb_max)
+
+
+class SphereEditor:
+    """mode: 'fill' (EditMode::kFill) or 'dig' (EditMode::kDig)."""
+
+    def __init__(self, center, r2, mode="fill"):
+        if mode not in ("fill", "dig"):
+            raise ValueError("GPU geometry editors: fill | dig (paint only changes colour: SURVEY §8f N2)")
+        self.desc = abi.sphere(center, r2, dig=(mode == "dig"))
+
+
+class TerrainEditor:
+    def __init__(self, voxel_level, seed=0x5EED, octaves=4):
+        self.desc = abi.terrain(voxel_level, seed, octaves)
+
+
+def _desc(e):
+    return e if isinstance(e, HdEditDesc) else e.desc
+
+
+class DAGNodePool:
+    """Device-resident hashed node pool (replaces src/DAGNodePool.{hpp,cpp} + the hashdag mix-ins it derives from)."""
+
+    def __init__(self, config, device=0):
+        self._h = C.c_void_p()
+        self._L = lib()
+        self.config = config
+        _check(self._L.hd_pool_create(C.byref(config), device, C.byref(self._h)))
+        self.device = device
+        self.last_stats = None
+
+    @classmethod
+    def Create(cls, config, device=0):
+        return cls(config, device)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.hd_pool_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- NodePoolBase surface --
+    def GetConfig(self):
+        return self.config
+
+    def SetRoot(self, root):
+        _check(self._L.hd_pool_set_root(self._h, root))
+
+    def GetRoot(self):
+        return self._L.hd_pool_get_root(self._h)
+
+    def Edit(self, root, editor):
+        """NodePoolBase::Edit (NodePool.hpp:405-417): one edit, returns the new root pointer."""
+        return self.EditBatch(root, [editor])
+
+    def ThreadedEdit(self, root, editor, max_task_level=None):
+        """NodePoolThreadedEdit::ThreadedEdit (NodePoolThreadedEdit.hpp:104-126).  The GPU path has no task level."""
+        return self.EditBatch(root, [editor])
+
+    def EditBatch(self, root, editors):
+        """Apply editors in order in one GPU pass (same canonical DAG as sequential reference Edit calls)."""
+        arr = edit_array([_desc(e) for e in editors])
+        out = C.c_uint32(root)
+        st = HdEditStats()
+        _check(self._L.hd_edit_batch(self._h, root, arr, len(editors), C.byref(out), C.byref(st)))
+        self.last_stats = st.as_dict()
+        return out.value
+
+    def Upsert(self, level, nodes, words_each):
+        """upsert_inner_node / upsert_leaf (NodePool.hpp:228-238) for n explicit packed nodes."""
+        a = np.ascontiguousarray(nodes, dtype=np.uint32).reshape(-1, words_each)
+        out = np.empty(a.shape[0], np.uint32)
+        _check(self._L.hd_upsert_nodes(self._h, level, a.ctypes.data, words_each, a.shape[0], out.ctypes.data))
+        return out
+
+    def FilledNodes(self):
+        out = (C.c_uint32 * self.config.node_levels)()
+        _check(self._L.hd_pool_filled_nodes(self._h, out))
+        return list(out)
+
+    def Traversal(self, root, o, d):
+        """NodePoolTraversal::Traversal<float> (NodePoolTraversal.hpp:93-256): float32 hit position or None."""
+        o3, d3, out, hit = (C.c_float * 3)(*o), (C.c_float * 3)(*d), (C.c_float * 3)(), C.c_int(0)
+        _check(self._L.hd_traverse_ray(self._h, root, o3, d3, C.byref(hit), out))
+        return np.array(out[:], dtype=np.float32) if hit.value else None
+
+    def Flush(self):
+        """DAGNodePool::Flush (src/DAGNodePool.cpp:56-85): device memory is the pool, so this only synchronises."""
+        _check(self._L.hd_sync(self._h))
+
+    def Clear(self):
+        _check(self._L.hd_pool_clear(self._h))
+
+    # -- host mirror interop (ReadPage / WritePage) --
+    def UploadWords(self, word_offset, words):
+        a = np.ascontiguousarray(words, dtype=np.uint32)
+        _check(self._L.hd_pool_upload_words(self._h, word_offset, a.ctypes.data, a.size))
+
+    def ReadWords(self, word_offset, count):
+        out = np.empty(count, np.uint32)
+        _check(self._L.hd_pool_read_words(self._h, word_offset, out.ctypes.data, count))
+        return out
+
+    def UploadBucketWords(self, first_bucket, values):
+        a = np.ascontiguousarray(values, dtype=np.uint32)
+        _check(self._L.hd_pool_upload_bucket_words(self._h, first_bucket, a.ctypes.data, a.size))
+
+    def ReadBucketWords(self):
+        out = np.empty(self.config.total_buckets(), np.uint32)
+        _check(self._L.hd_pool_read_bucket_words(self._h, 0, out.ctypes.data, out.size))
+        return out
+
+    def UploadFrom(self, host_pool):
+        """Mirror a host pool (anything with used_ranges()/words_np()/bucket_words_np()) onto the device."""
+        for off, cnt in host_pool.used_ranges():
+            self.UploadWords(off, host_pool.words_np(off, cnt))
+        self.UploadBucketWords(0, host_pool.bucket_words_np())
+
+    def Download(self):
+        """(words_by_range dict, bucket_words): used prefix of every non-empty bucket, read back to the host."""
+        bw = self.ReadBucketWords()
+        shift = self.config.word_bits_per_page + self.config.page_bits_per_bucket
+        return {int(b) << shift: self.ReadWords(int(b) << shift, int(bw[b])) for b in np.nonzero(bw)[0]}, bw
+
+    def UsedWords(self):
+        out = C.c_uint64()
+        _check(self._L.hd_pool_used_words(self._h, C.byref(out)))
+        return out.value
+
+    def UploadColor(self, color_nodes, color_leaves):
+        n = np.ascontiguousarray(color_nodes, dtype=np.uint32)
+        l = np.ascontiguousarray(color_leaves, dtype=np.uint32)
+        _check(self._L.hd_color_upload(self._h, n.ctypes.data, n.size, l.ctypes.data, l.size))
+
+    # -- trace --
+    def Trace(self, params, want=("rgba8", "hits", "iters"), shard=None, out=None):
+        """One frame through hd_trace / hd_trace_tiles with HOST outputs.  Returns dict of numpy arrays."""
+        if shard is None:
+            n = params.width * params.height
+            shape = (params.height, params.width)
+        else:
+            shard = HdTileShard(*shard) if not isinstance(shard, HdTileShard) else shard
+            n = int(self._L.hd_tile_shard_pixels(C.byref(params), C.byref(shard)))
+            shape = (n,)
+        res = out or {}
+        if "rgba8" in want and "rgba8" not in res:
+            res["rgba8"] = np.zeros(shape, np.uint32)
+        if "hits" in want and "hits" not in res:
+            res["hits"] = np.zeros(shape, HIT_DTYPE)
+        if "iters" in want and "iters" not in res:
+            res["iters"] = np.zeros(shape, np.uint32)
+        o = HdTraceOutputs(res["rgba8"].ctypes.data if "rgba8" in want else None,
+                           res["hits"].ctypes.data if "hits" in want else None,
+                           res["iters"].ctypes.data if "iters" in want else None)
+        if shard is None:
+            _check(self._L.hd_trace(self._h, C.byref(params), C.byref(o)))
+        else:
+            _check(self._L.hd_trace_tiles(self._h, C.byref(params), C.byref(shard), C.byref(o)))
+        return res
+
+    def TraceDev(self, params, rgba8=0, hits=0, iters=0, shard=None):
+        """Enqueue one frame with DEVICE output pointers (ints, e.g. torch.Tensor.data_ptr()); no synchronisation."""
+        o = HdTraceOutputs(rgba8 or None, hits or None, iters or None)
+        if shard is None:
+            _check(self._L.hd_trace_dev(self._h, C.byref(params), C.byref(o)))
+        else:
+            shard = HdTileShard(*shard) if not isinstance(shard, HdTileShard) else shard
+            _check(self._L.hd_trace_tiles_dev(self._h, C.byref(params), C.byref(shard), C.byref(o)))
+
+    def ShardPixels(self, params, shard):
+        shard = HdTileShard(*shard) if not isinstance(shard, HdTileShard) else shard
+        return int(self._L.hd_tile_shard_pixels(C.byref(params), C.byref(shard)))
+
+    def Sync(self):
+        _check(self._L.hd_sync(self._h))
+
+    @property
+    def stream(self):
+        return self._L.hd_pool_stream(self._h)
+
+    @property
+    def words_dev(self):
+        return self._L.hd_pool_words_dev(self._h)
+
+    # -- replica sync --
+    def DirtyCount(self):
+        n, b = C.c_uint32(), C.c_uint64()
+        _check(self._L.hd_dirty_count(self._h, C.byref(n), C.byref(b)))
+        return n.value, b.value
+
+    def DirtyRanges(self):
+        n, _ = self.DirtyCount()
+        arr = (HdDirtyRange * max(n, 1))()
+        got = C.c_uint32()
+        _check(self._L.hd_dirty_ranges(self._h, arr, n, C.byref(got)))
+        return [(arr[i].word_offset, arr[i].word_count) for i in range(min(n, got.value))]
+
+    def DirtyPack(self, staging_dev_ptr, capacity_bytes):
+        b = C.c_uint64()
+        _check(self._L.hd_dirty_pack_dev(self._h, staging_dev_ptr, capacity_bytes, C.byref(b)))
+        return b.value
+
+    def DirtyApply(self, staging_dev_ptr, packed_bytes):
+        _check(self._L.hd_dirty_apply_dev(self._h, staging_dev_ptr, packed_bytes))
+
+    def DirtyReset(self):
+        _check(self._L.hd_dirty_reset(self._h))

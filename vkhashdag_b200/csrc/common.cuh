@@ -1,0 +1,97 @@
+// common.cuh — shared host/device declarations of libhashdag_b200.so (sm_100a only, no CPU fallback).
+#pragma once
+#include "../../include/hashdag_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace hd {
+
+constexpr uint32_t kNull = HD_NULL_NODE;
+
+// ---- error plumbing -----------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define HD_CUDA_TRY(expr)                                                                                              \
+	do {                                                                                                               \
+		cudaError_t _e = (expr);                                                                                       \
+		if (_e != cudaSuccess) {                                                                                       \
+			hd::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);                 \
+			return _e == cudaErrorMemoryAllocation ? HD_ERR_OOM : HD_ERR_CUDA;                                         \
+		}                                                                                                              \
+	} while (0)
+
+#define HD_LAUNCH_CHECK()                                                                                              \
+	do {                                                                                                               \
+		hd::g_launches.fetch_add(1, std::memory_order_relaxed);                                                        \
+		HD_CUDA_TRY(cudaGetLastError());                                                                               \
+	} while (0)
+
+// ---- pool geometry (include/hashdag/Config.hpp:15-57), passed to kernels by value -----------------
+struct Geometry {
+	uint32_t word_bits_per_page;
+	uint32_t page_bits_per_bucket;
+	uint32_t node_levels;
+	uint32_t bucket_bits[HD_MAX_NODE_LEVELS];
+	uint32_t level_base[HD_MAX_NODE_LEVELS]; // Config.hpp:33-38
+	uint32_t total_buckets;
+	uint64_t total_words;
+
+	__host__ __device__ uint32_t words_per_page() const { return 1u << word_bits_per_page; }
+	__host__ __device__ uint32_t bucket_shift() const { return word_bits_per_page + page_bits_per_bucket; }
+	__host__ __device__ uint32_t words_per_bucket() const { return 1u << bucket_shift(); }
+	__host__ __device__ uint32_t voxel_level() const { return node_levels + 1u; }
+	__host__ __device__ uint32_t level_of_bucket(uint32_t bucket) const {
+		uint32_t l = 0;
+		while (l + 1 < node_levels && bucket >= level_base[l + 1])
+			++l;
+		return l;
+	}
+};
+
+bool make_geometry(const hd_config &cfg, Geometry &g);
+
+struct EditScratch; // edit.cu
+
+} // namespace hd
+
+// The opaque pool handle of the C ABI.
+struct hd_pool {
+	hd_config cfg{};
+	hd::Geometry geo{};
+	int device = 0;
+	cudaStream_t stream = nullptr;
+
+	uint32_t *words = nullptr;        // flat word space, SURVEY App. A.1 (device)
+	uint32_t *bucket_words = nullptr; // used words per bucket incl. page padding (device)
+	uint32_t *bucket_synced = nullptr; // bucket_words at the last hd_dirty_reset (device)
+
+	uint32_t *color_nodes = nullptr, *color_leaves = nullptr; // DAGColorPool buffers (device)
+	uint64_t color_node_words = 0, color_leaf_words = 0;
+
+	uint32_t root = HD_NULL_NODE;
+	std::vector<uint32_t> filled; // m_filled_node_pointers (NodePool.hpp:54)
+
+	// trace staging (device) for the host-pointer entry points
+	uint32_t *stage_rgba = nullptr, *stage_iters = nullptr;
+	hd_hit_record *stage_hits = nullptr;
+	uint64_t stage_pixels = 0;
+	hd_trace_params *params_dev = nullptr;
+
+	hd::EditScratch *edit = nullptr;
+
+	// dirty-range scratch
+	uint32_t *dirty_scratch = nullptr; // [0]=n_ranges, [1]=payload words, then per-range data
+	uint64_t dirty_scratch_bytes = 0;
+};
+
+namespace hd {
+hd_status edit_scratch_free(hd_pool *pool);
+hd_status ensure_filled(hd_pool *pool);
+} // namespace hd

@@ -1,0 +1,883 @@
+// edit.cu — kernel family #2: batched, level-synchronous edit rebuild on the GPU (sm_100a).
+//
+// Replaces the libfork CPU editor: NodePoolBase::Edit / edit_node / edit_leaf / upsert_node
+// (include/hashdag/NodePool.hpp:159-212,319-417) under NodePoolThreadedEdit (NodePoolThreadedEdit.hpp:27-126).
+//
+// The reference recurses depth-first, one edit at a time.  Here a whole batch of edits is applied in ONE
+// breadth-first pass:
+//   top-down  (k_down)      every work item (node that some edit must enter) classifies its 8 children against
+//                           its ordered edit list (EditNode, NodePool.hpp:345-360).  A kFill/kClear replaces the
+//                           child by the filled node / Null and discards the earlier edits of the list (exactly
+//                           what sequential application would leave); kNotAffected edits are dropped; the kProceed
+//                           edits that remain form the child's list.  Children with an empty list are final.
+//   leaves    (k_leaf)      one warp per 4x4x4 leaf: 64 EditVoxel evaluations per listed edit (NodePool.hpp:319-343).
+//   bottom-up (k_assemble)  re-pack changed nodes (NodePool.hpp:362-396), then find-or-insert them:
+//       k_dedup   in-batch dedup through a scratch open-addressing table (one winner per distinct content),
+//       k_upsert  one warp per winner: coalesced scan of the bucket (find_node, NodePool.hpp:79-132) and, on a
+//                 miss, a lock-free CAS reservation in the bucket honouring the no-page-straddle rule
+//                 (append_node, NodePool.hpp:134-157),
+//       k_resolve losers take their winner's pointer; results flow to the parent's child slots.
+// Phase separation makes the append log safe without locks: a bucket scan can only miss nodes whose content
+// differs from the scanner's (equal contents were merged by k_dedup), and reserved-but-unwritten words are
+// zero or partial and can never equal a candidate.  The final voxel set equals sequential application of the
+// batch, hence the canonical DAG is identical to the reference's; pointer values are not.
+#include "common.cuh"
+#include "editors.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace hd {
+
+constexpr uint32_t kPending = 0xFFFFFFFEu; // placeholder in child_new until the child item reports
+constexpr int kBlock = 256;
+
+struct DevCounters {
+	unsigned long long stats[8]; // visited_nodes, visited_leaves, upserts, appended_nodes, appended_words, overflow, -, scan_words
+	uint32_t next_items;
+	uint32_t next_entries;
+	uint32_t root_out;
+	uint32_t error; // 1 = scratch overflow
+};
+
+// One BFS level of work items (device arrays, SoA).
+struct LevelView {
+	uint32_t n;          // items
+	uint32_t cap;        // item capacity
+	uint32_t cap_entries;
+	uint32_t *cur;       // current node pointer of the item (after Fill/Clear substitution)
+	uint64_t *pos;       // packed node coordinates x | y<<21 | z<<42
+	uint32_t *list_off;  // first entry in `lists`
+	uint32_t *list_len;
+	uint32_t *parent;    // (parent item << 3) | child slot; 0xFFFFFFFF for the root item
+	uint32_t *result;    // new pointer of the item
+	uint32_t *child_new; // [n*8] new child pointers (inner levels)
+	uint32_t *lists;     // edit indices, ascending (= application order)
+	// upsert candidates
+	uint32_t *cand;      // [n*stride] packed node words
+	uint8_t *state;      // 0 = final, 1 = candidate (winner or loser), 2 = winner
+	uint32_t *winner;    // winner item of a loser
+};
+
+struct EditScratch {
+	DevCounters *ctr = nullptr;
+	uint32_t *filled_dev = nullptr;
+	bool fast_scan = true;
+};
+
+__device__ __forceinline__ uint64_t pack_pos(uint32_t x, uint32_t y, uint32_t z) {
+	return uint64_t(x) | (uint64_t(y) << 21) | (uint64_t(z) << 42);
+}
+__device__ __forceinline__ void unpack_pos(uint64_t p, uint32_t &x, uint32_t &y, uint32_t &z) {
+	x = uint32_t(p) & 0x1FFFFFu, y = uint32_t(p >> 21) & 0x1FFFFFu, z = uint32_t(p >> 42) & 0x1FFFFFu;
+}
+
+// ---- hashing: include/hashdag/Hasher.hpp:21-49 -------------------------------------------------------
+__device__ __forceinline__ uint32_t rotl32(uint32_t v, int s) { return __funnelshift_l(v, v, s); }
+__device__ __forceinline__ uint32_t hash_inner(const uint32_t *w, uint32_t n) {
+	uint32_t h = 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		uint32_t k = w[i] * 0xcc9e2d51u;
+		k = rotl32(k, 15) * 0x1b873593u;
+		h = rotl32(h ^ k, 13) * 5u + 0xe6546b64u;
+	}
+	h ^= n;
+	return fmix32(h);
+}
+__device__ __forceinline__ uint32_t hash_leaf(uint32_t w0, uint32_t w1) {
+	uint64_t h = uint64_t(w0) | (uint64_t(w1) << 32);
+	h ^= h >> 33;
+	h *= 0xff51afd7ed558ccdull;
+	h ^= h >> 33;
+	h *= 0xc4ceb9fe1a85ec53ull;
+	h ^= h >> 33;
+	return uint32_t(h);
+}
+__device__ __forceinline__ uint64_t mix64(uint64_t h) {
+	h ^= h >> 30;
+	h *= 0xbf58476d1ce4e5b9ull;
+	h ^= h >> 27;
+	h *= 0x94d049bb133111ebull;
+	h ^= h >> 31;
+	return h;
+}
+
+// ---- edit-list filtering for one (node, child) pair ------------------------------------------------------
+// Scans the parent's list from the back: the last kFill/kClear decides the child's base pointer, the kProceed
+// edits after it survive.  Lists of <= 32 entries are evaluated once (decisions cached in a mask).
+struct Filtered {
+	uint32_t cur, count, start, keep;
+};
+// An edit that cannot change a subtree in its current state: digging empty space, or filling a filled node
+// (the reference recursion returns the same pointer in both cases, NodePool.hpp:340-342,391-395).
+__device__ __forceinline__ bool is_noop(uint32_t kind, uint32_t cur, uint32_t filled_ptr) {
+	return kind == HD_EDIT_SPHERE_DIG ? cur == kNull : cur == filled_ptr;
+}
+__device__ inline Filtered filter_list(const hd_edit_desc *__restrict__ edits, const uint32_t *__restrict__ list,
+                                       uint32_t len, uint32_t bits, uint32_t x, uint32_t y, uint32_t z, uint32_t cur,
+                                       uint32_t filled_ptr) {
+	Filtered f{cur, 0u, 0u, 0u};
+	int j = int(len) - 1;
+	for (; j >= 0; --j) {
+		const EditType t = edit_node(edits[list[j]], bits, x, y, z);
+		if (t == kFill) {
+			f.cur = filled_ptr;
+			break;
+		}
+		if (t == kClear) {
+			f.cur = kNull;
+			break;
+		}
+		if (t == kProceed) {
+			++f.count;
+			if (len <= 32)
+				f.keep |= 1u << j;
+		}
+	}
+	f.start = uint32_t(j + 1);
+	// drop leading edits that are no-ops on the base state
+	if (f.count && (f.cur == kNull || f.cur == filled_ptr)) {
+		if (len <= 32) {
+			while (f.keep) {
+				const uint32_t k = __ffs(f.keep) - 1;
+				if (!is_noop(edits[list[k]].kind, f.cur, filled_ptr))
+					break;
+				f.keep &= f.keep - 1;
+				--f.count;
+				f.start = k + 1;
+			}
+		} else {
+			while (f.count) {
+				const hd_edit_desc &e = edits[list[f.start]];
+				const bool proceed = edit_node(e, bits, x, y, z) == kProceed;
+				if (proceed && !is_noop(e.kind, f.cur, filled_ptr))
+					break;
+				if (proceed)
+					--f.count;
+				++f.start;
+			}
+		}
+	}
+	return f;
+}
+__device__ inline void write_list(const hd_edit_desc *__restrict__ edits, const uint32_t *__restrict__ list, uint32_t len,
+                                  uint32_t bits, uint32_t x, uint32_t y, uint32_t z, const Filtered &f, uint32_t *dst) {
+	if (len <= 32) {
+		uint32_t keep = f.keep;
+		while (keep) {
+			const uint32_t j = __ffs(keep) - 1;
+			keep &= keep - 1;
+			*dst++ = list[j];
+		}
+	} else {
+		for (uint32_t j = f.start; j < len; ++j)
+			if (edit_node(edits[list[j]], bits, x, y, z) == kProceed)
+				*dst++ = list[j];
+	}
+}
+
+// Allocate one slot in the next level (and `count` list entries) with warp-aggregated atomics.
+// Must be called by all 32 lanes of the warp (lanes without work pass want = false).
+__device__ __forceinline__ bool alloc_item(DevCounters *ctr, bool want, uint32_t count, uint32_t cap, uint32_t cap_entries,
+                                           uint32_t &item, uint32_t &entry_off) {
+	const uint32_t full = 0xFFFFFFFFu;
+	const uint32_t wants = __ballot_sync(full, want);
+	if (!wants)
+		return false;
+	const uint32_t lane = threadIdx.x & 31u;
+	uint32_t c = want ? count : 0u, scan = c; // inclusive warp scan of the list lengths
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t v = __shfl_up_sync(full, scan, d);
+		if (lane >= uint32_t(d))
+			scan += v;
+	}
+	const uint32_t total_entries = __shfl_sync(full, scan, 31);
+	uint32_t base_item = 0, base_entry = 0;
+	if (lane == 0) {
+		base_item = atomicAdd(&ctr->next_items, __popc(wants));
+		base_entry = atomicAdd(&ctr->next_entries, total_entries);
+	}
+	base_item = __shfl_sync(full, base_item, 0);
+	base_entry = __shfl_sync(full, base_entry, 0);
+	item = base_item + __popc(wants & ((1u << lane) - 1u));
+	entry_off = base_entry + scan - c;
+	if (want && (item >= cap || entry_off + count > cap_entries)) {
+		ctr->error = 1;
+		return false;
+	}
+	return want;
+}
+
+// Root classification (edit_switch on the root, NodePool.hpp:405-413).  One thread.
+__global__ void k_root(Geometry g, const hd_edit_desc *__restrict__ edits, uint32_t n_edits,
+                       const uint32_t *__restrict__ iota, const uint32_t *__restrict__ filled, uint32_t root,
+                       LevelView out, DevCounters *ctr) {
+	if (threadIdx.x != 0 || blockIdx.x != 0)
+		return;
+	const uint32_t bits = g.voxel_level();
+	Filtered f = filter_list(edits, iota, n_edits, bits, 0, 0, 0, root, filled[0]);
+	if (f.count == 0) {
+		ctr->root_out = f.cur;
+		return;
+	}
+	ctr->next_items = 1;
+	ctr->next_entries = f.count;
+	out.cur[0] = f.cur;
+	out.pos[0] = 0;
+	out.parent[0] = 0xFFFFFFFFu;
+	out.list_off[0] = 0;
+	out.list_len[0] = f.count;
+	write_list(edits, iota, n_edits, bits, 0, 0, 0, f, out.lists);
+}
+
+// Top-down expansion: thread per (item, child).
+__global__ void __launch_bounds__(kBlock) k_down(Geometry g, uint32_t level /* of `in` */,
+                                                 const uint32_t *__restrict__ words,
+                                                 const hd_edit_desc *__restrict__ edits,
+                                                 const uint32_t *__restrict__ filled, LevelView in, LevelView out,
+                                                 DevCounters *ctr) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t item = t >> 3, c = t & 7u;
+	const bool valid = item < in.n;
+	Filtered f{kNull, 0u, 0u, 0u};
+	uint32_t x = 0, y = 0, z = 0, len = 0;
+	const uint32_t *list = nullptr;
+	const uint32_t bits = g.voxel_level() - (level + 1u);
+	if (valid) {
+		const uint32_t cur = in.cur[item];
+		uint32_t child = kNull;
+		if (cur != kNull) { // get_unpacked_node_array, NodePool.hpp:278-309
+			const uint32_t mask = words[cur];
+			if (mask >> c & 1u)
+				child = words[cur + 1u + __popc(mask & ((1u << c) - 1u))];
+		}
+		unpack_pos(in.pos[item], x, y, z);
+		x = (x << 1) | (c & 1u), y = (y << 1) | ((c >> 1) & 1u), z = (z << 1) | ((c >> 2) & 1u); // NodeCoord.hpp:18-28
+		list = in.lists + in.list_off[item];
+		len = in.list_len[item];
+		f = filter_list(edits, list, len, bits, x, y, z, child, filled[level + 1u]);
+	}
+	uint32_t slot, entry_off;
+	const bool made = alloc_item(ctr, valid && f.count != 0, f.count, out.cap, out.cap_entries, slot, entry_off);
+	if (!valid)
+		return;
+	if (made) {
+		out.cur[slot] = f.cur;
+		out.pos[slot] = pack_pos(x, y, z);
+		out.parent[slot] = (item << 3) | c;
+		out.list_off[slot] = entry_off;
+		out.list_len[slot] = f.count;
+		write_list(edits, list, len, bits, x, y, z, f, out.lists + entry_off);
+		in.child_new[size_t(item) * 8u + c] = kPending;
+	} else {
+		in.child_new[size_t(item) * 8u + c] = f.cur;
+	}
+}
+
+// Leaf pass: one warp per leaf item; lane l owns voxels l and l+32 (NodeCoord::GetLeafCoord, NodeCoord.hpp:32-43).
+__global__ void __launch_bounds__(kBlock) k_leaf(Geometry g, const uint32_t *__restrict__ words,
+                                                 const hd_edit_desc *__restrict__ edits, LevelView lv,
+                                                 DevCounters *ctr) {
+	const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+	if (item >= lv.n)
+		return;
+	const uint32_t cur = lv.cur[item];
+	uint32_t w0 = 0, w1 = 0;
+	if (cur != kNull)
+		w0 = words[cur], w1 = words[cur + 1];
+	uint32_t x, y, z;
+	unpack_pos(lv.pos[item], x, y, z);
+	const uint32_t vx = (x << 2) | ((lane >> 2) & 2u) | (lane & 1u);
+	const uint32_t vy = (y << 2) | ((lane >> 3) & 2u) | ((lane >> 1) & 1u);
+	const uint32_t vz = (z << 2) | ((lane >> 2) & 1u); // voxel l: z1 = 0; voxel l+32: z1 = 1 (adds 2)
+	bool a = w0 >> lane & 1u, b = w1 >> lane & 1u;
+	const uint32_t *list = lv.lists + lv.list_off[item];
+	const uint32_t len = lv.list_len[item];
+	for (uint32_t j = 0; j < len; ++j) {
+		const hd_edit_desc &e = edits[list[j]];
+		a = edit_voxel(e, vx, vy, vz, a);
+		b = edit_voxel(e, vx, vy, vz + 2u, b);
+	}
+	const uint32_t n0 = __ballot_sync(0xFFFFFFFFu, a), n1 = __ballot_sync(0xFFFFFFFFu, b);
+	if (lane == 0) {
+		uint8_t st = 0;
+		uint32_t res = cur;
+		if (n0 != w0 || n1 != w1) { // changed
+			if ((n0 | n1) == 0u)
+				res = kNull;
+			else {
+				st = 1;
+				lv.cand[size_t(item) * 2u] = n0;
+				lv.cand[size_t(item) * 2u + 1u] = n1;
+			}
+		}
+		lv.state[item] = st;
+		lv.result[item] = res;
+	}
+}
+
+// Bottom-up re-pack of inner items (edit_node tail, NodePool.hpp:384-395).  Thread per item.
+__global__ void __launch_bounds__(kBlock) k_assemble(const uint32_t *__restrict__ words, LevelView lv) {
+	const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+	if (item >= lv.n)
+		return;
+	const uint32_t cur = lv.cur[item];
+	uint32_t old_mask = 0;
+	if (cur != kNull)
+		old_mask = words[cur];
+	uint32_t packed[9], k = 1, mask = 0, oi = 1;
+	bool changed = false;
+	for (uint32_t c = 0; c < 8; ++c) {
+		uint32_t oldc = kNull;
+		if (old_mask >> c & 1u)
+			oldc = words[cur + oi++];
+		const uint32_t newc = lv.child_new[size_t(item) * 8u + c];
+		changed |= newc != oldc;
+		if (newc != kNull) {
+			mask |= 1u << c;
+			packed[k++] = newc;
+		}
+	}
+	packed[0] = mask;
+	uint8_t st = 0;
+	uint32_t res = cur;
+	if (changed) {
+		if (mask == 0)
+			res = kNull;
+		else {
+			st = 1;
+			for (uint32_t i = 0; i < k; ++i)
+				lv.cand[size_t(item) * 9u + i] = packed[i];
+		}
+	}
+	lv.state[item] = st;
+	lv.result[item] = res;
+}
+
+// In-batch dedup: one winner per distinct candidate content.  Thread per item.
+__global__ void __launch_bounds__(kBlock) k_dedup(uint32_t n, uint32_t stride, bool is_leaf,
+                                                  const uint32_t *__restrict__ cand, uint8_t *state, uint32_t *winner,
+                                                  uint32_t *table, uint32_t table_mask) {
+	const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+	if (item >= n || state[item] == 0)
+		return;
+	const uint32_t *me = cand + size_t(item) * stride;
+	const uint32_t nw = is_leaf ? 2u : 1u + __popc(me[0] & 0xFFu);
+	uint64_t h = 0x9e3779b97f4a7c15ull;
+	for (uint32_t i = 0; i < nw; ++i)
+		h = mix64(h ^ me[i]) + i;
+	uint32_t slot = uint32_t(h >> 20) & table_mask;
+	for (;;) {
+		uint32_t v = table[slot];
+		if (v == 0u) {
+			v = atomicCAS(&table[slot], 0u, item + 1u);
+			if (v == 0u) {
+				state[item] = 2; // winner
+				return;
+			}
+		}
+		const uint32_t *other = cand + size_t(v - 1u) * stride;
+		bool same = true;
+		for (uint32_t i = 0; i < nw && same; ++i)
+			same = other[i] == me[i];
+		if (same) {
+			winner[item] = v - 1u;
+			return;
+		}
+		slot = (slot + 1u) & table_mask;
+	}
+}
+
+// Find-or-insert of every winner: warps stride over the items (persistent grid), one warp per item at a time.
+// find_node + append_node, NodePool.hpp:79-157,159-212.
+__global__ void __launch_bounds__(kBlock) k_upsert(Geometry g, uint32_t level, bool fast_scan, uint32_t n,
+                                                   uint32_t stride, const uint32_t *__restrict__ cand,
+                                                   const uint8_t *__restrict__ state, const uint32_t *__restrict__ fallback,
+                                                   uint32_t *result, uint32_t *words, uint32_t *bucket_words,
+                                                   DevCounters *ctr) {
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+	const bool is_leaf = level == g.node_levels - 1u;
+	const uint32_t wpp = g.words_per_page(), wpb = g.words_per_bucket();
+	unsigned long long st_upserts = 0, st_nodes = 0, st_words = 0, st_overflow = 0, st_scan = 0; // lane 0 only
+
+	for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n; item += warps) {
+		if (state[item] != 2)
+			continue;
+		const uint32_t *me = cand + size_t(item) * stride;
+		const uint32_t c0 = me[0], c1 = me[1];
+		const uint32_t nw = is_leaf ? 2u : 1u + __popc(c0 & 0xFFu);
+		const uint32_t h = is_leaf ? hash_leaf(c0, c1) : hash_inner(me, nw);
+		const uint32_t bucket = g.level_base[level] + (h & ((1u << g.bucket_bits[level]) - 1u)); // NodePool.hpp:163-164
+		const uint32_t base = bucket << g.bucket_shift();
+		const uint32_t bw = *reinterpret_cast<volatile uint32_t *>(bucket_words + bucket);
+
+		uint32_t found = kNull;
+		if (is_leaf) {
+			// leaves are 2-word aligned: each lane compares one pair per 64-word chunk
+			for (uint32_t off = 0; off < bw; off += 64u) {
+				const uint32_t p = off + lane * 2u;
+				bool hit = false;
+				if (p + 2u <= bw) {
+					const uint2 w = *reinterpret_cast<const uint2 *>(words + base + p);
+					hit = w.x == c0 && w.y == c1;
+				}
+				const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+				if (m) {
+					found = base + off + (__ffs(m) - 1u) * 2u;
+					break;
+				}
+			}
+		} else if (fast_scan) {
+			// A word <= 0xFF inside a used bucket region is always a node header (child pointers are >= 256
+			// here), so every position can be tested independently: header match, then the children.
+			for (uint32_t off = 0; off < bw; off += 32u) {
+				const uint32_t p = off + lane;
+				bool hit = false;
+				if (p + nw <= bw && words[base + p] == c0) {
+					hit = true;
+					for (uint32_t i = 1; i < nw && hit; ++i)
+						hit = words[base + p + i] == me[i];
+				}
+				const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+				if (m) {
+					found = base + off + __ffs(m) - 1u;
+					break;
+				}
+			}
+		} else {
+			if (lane == 0) { // tiny configs where a child pointer may look like a header: sequential walk
+				for (uint32_t page = 0; page < bw && found == kNull; page += wpp) {
+					const uint32_t end = min(page + wpp, bw);
+					for (uint32_t it = page; nw <= end - it;) {
+						const uint32_t hw = words[base + it] & 0xFFu;
+						if (hw == 0u)
+							break;
+						const uint32_t sz = 1u + __popc(hw);
+						bool same = sz == nw;
+						for (uint32_t i = 0; i < nw && same; ++i)
+							same = words[base + it + i] == me[i];
+						if (same) {
+							found = base + it;
+							break;
+						}
+						it += sz;
+					}
+				}
+			}
+			found = __shfl_sync(0xFFFFFFFFu, found, 0);
+		}
+
+		if (lane == 0) {
+			if (found == kNull) {
+				// append_node: lock-free reservation; a node never straddles a page, the skipped tail stays zero
+				uint32_t old = bw;
+				for (;;) {
+					const uint32_t off = old & (wpp - 1u);
+					const uint32_t at = off + nw > wpp ? (old | (wpp - 1u)) + 1u : old;
+					if (at + nw > wpb) { // bucket full: NodePool.hpp:137-139,195 -> keep the old node
+						found = fallback ? fallback[item] : kNull;
+						++st_overflow;
+						break;
+					}
+					const uint32_t prev = atomicCAS(bucket_words + bucket, old, at + nw);
+					if (prev == old) {
+						for (uint32_t i = 0; i < nw; ++i)
+							words[base + at + i] = me[i];
+						found = base + at;
+						++st_nodes;
+						st_words += at + nw - old;
+						break;
+					}
+					old = prev;
+				}
+			}
+			result[item] = found;
+			++st_upserts;
+			st_scan += bw;
+		}
+		__syncwarp();
+	}
+	if (lane == 0 && st_upserts) {
+		atomicAdd(&ctr->stats[2], st_upserts);
+		atomicAdd(&ctr->stats[7], st_scan);
+		if (st_nodes) {
+			atomicAdd(&ctr->stats[3], st_nodes);
+			atomicAdd(&ctr->stats[4], st_words);
+		}
+		if (st_overflow)
+			atomicAdd(&ctr->stats[5], st_overflow);
+	}
+}
+
+// Losers copy their winner's pointer; every item reports to its parent's child slot (or the root output).
+__global__ void __launch_bounds__(kBlock) k_resolve(LevelView lv, uint32_t *parent_child_new, DevCounters *ctr) {
+	const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+	if (item >= lv.n)
+		return;
+	uint32_t res = lv.result[item];
+	if (lv.state[item] == 1)
+		res = lv.result[lv.winner[item]];
+	const uint32_t par = lv.parent[item];
+	if (par == 0xFFFFFFFFu)
+		ctr->root_out = res;
+	else
+		parent_child_new[par] = res;
+}
+
+__global__ void k_resolve_flat(uint32_t n, const uint8_t *__restrict__ state, const uint32_t *__restrict__ winner,
+                               uint32_t *result) {
+	const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+	if (item < n && state[item] == 1)
+		result[item] = result[winner[item]];
+}
+
+__global__ void k_iota(uint32_t *out, uint32_t n) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n)
+		out[i] = i;
+}
+__global__ void k_fill_u8(uint8_t *out, uint32_t n, uint8_t v) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n)
+		out[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static inline uint32_t grid_for(uint64_t threads) { return uint32_t((threads + kBlock - 1) / kBlock); }
+// persistent grid for warp-per-item kernels: a multiple of the SM count, capped by the work
+static inline uint32_t upsert_grid(hd_pool *p, uint32_t n) {
+	static int sms = 0;
+	if (!sms)
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+	const uint64_t need = (uint64_t(n) * 32 + kBlock - 1) / kBlock;
+	return uint32_t(std::min<uint64_t>(need, uint64_t(sms) * 8));
+}
+
+template <typename T> static cudaError_t amalloc(T **p, uint64_t count, cudaStream_t s) {
+	return cudaMallocAsync(reinterpret_cast<void **>(p), std::max<uint64_t>(count, 1) * sizeof(T), s);
+}
+
+struct LevelAlloc {
+	LevelView v{};
+	cudaStream_t s = nullptr;
+	cudaError_t init(uint32_t cap, uint32_t cap_entries, bool leaf, cudaStream_t stream) {
+		s = stream;
+		v.cap = cap, v.cap_entries = cap_entries, v.n = 0;
+		cudaError_t e;
+		if ((e = amalloc(&v.cur, cap, s)) || (e = amalloc(&v.pos, cap, s)) || (e = amalloc(&v.list_off, cap, s)) ||
+		    (e = amalloc(&v.list_len, cap, s)) || (e = amalloc(&v.parent, cap, s)) || (e = amalloc(&v.lists, cap_entries, s)))
+			return e;
+		(void)leaf;
+		return cudaSuccess;
+	}
+	// arrays only needed once the item count is known
+	cudaError_t init_up(bool leaf) {
+		cudaError_t e;
+		if ((e = amalloc(&v.result, v.n, s)) || (e = amalloc(&v.state, v.n, s)) || (e = amalloc(&v.winner, v.n, s)) ||
+		    (e = amalloc(&v.cand, uint64_t(v.n) * (leaf ? 2 : 9), s)))
+			return e;
+		if (!leaf && (e = amalloc(&v.child_new, uint64_t(v.n) * 8, s)))
+			return e;
+		return cudaSuccess;
+	}
+	void release() {
+		void *ptrs[] = {v.cur, v.pos, v.list_off, v.list_len, v.parent, v.lists, v.result, v.state, v.winner, v.cand, v.child_new};
+		for (void *p : ptrs)
+			if (p)
+				cudaFreeAsync(p, s);
+		v = LevelView{};
+	}
+};
+
+static hd_status scratch_init(hd_pool *p) {
+	if (p->edit)
+		return HD_OK;
+	auto *s = new EditScratch();
+	p->edit = s;
+	HD_CUDA_TRY(cudaMalloc(&s->ctr, sizeof(DevCounters)));
+	HD_CUDA_TRY(cudaMalloc(&s->filled_dev, sizeof(uint32_t) * HD_MAX_NODE_LEVELS));
+	// child pointers of any level >= 1 are >= (buckets at level 0) << bucket_shift
+	s->fast_scan = (uint64_t(1) << (p->geo.bucket_bits[0] + p->geo.bucket_shift())) >= 256ull;
+	return HD_OK;
+}
+
+hd_status edit_scratch_free(hd_pool *p) {
+	if (!p->edit)
+		return HD_OK;
+	cudaFree(p->edit->ctr);
+	cudaFree(p->edit->filled_dev);
+	delete p->edit;
+	p->edit = nullptr;
+	return HD_OK;
+}
+
+// dedup + find-or-insert + resolve over n candidates (state!=0) at `level`.
+static hd_status run_upsert(hd_pool *p, uint32_t level, uint32_t n, uint32_t stride, const uint32_t *cand,
+                            uint8_t *state, uint32_t *winner, const uint32_t *fallback, uint32_t *result) {
+	if (n == 0)
+		return HD_OK;
+	EditScratch *s = p->edit;
+	const bool is_leaf = level == p->geo.node_levels - 1;
+	uint64_t tsize = 64;
+	while (tsize < uint64_t(n) * 2)
+		tsize <<= 1;
+	uint32_t *table = nullptr;
+	HD_CUDA_TRY(amalloc(&table, tsize, p->stream));
+	HD_CUDA_TRY(cudaMemsetAsync(table, 0, tsize * 4, p->stream));
+	k_dedup<<<grid_for(n), kBlock, 0, p->stream>>>(n, stride, is_leaf, cand, state, winner, table, uint32_t(tsize - 1));
+	HD_LAUNCH_CHECK();
+	k_upsert<<<upsert_grid(p, n), kBlock, 0, p->stream>>>(p->geo, level, s->fast_scan, n, stride, cand, state,
+	                                                               fallback, result, p->words, p->bucket_words, s->ctr);
+	HD_LAUNCH_CHECK();
+	HD_CUDA_TRY(cudaFreeAsync(table, p->stream));
+	return HD_OK;
+}
+
+hd_status ensure_filled(hd_pool *p) { // make_filled_node_pointers, NodePool.hpp:240-262
+	if (!p->filled.empty())
+		return HD_OK;
+	HD_CUDA_TRY(cudaSetDevice(p->device));
+	hd_status st = scratch_init(p);
+	if (st != HD_OK)
+		return st;
+	const uint32_t L = p->geo.node_levels;
+	std::vector<uint32_t> filled(L, kNull);
+	uint32_t prev = kNull;
+	for (uint32_t l = L; l-- > 0;) {
+		uint32_t node[9];
+		uint32_t words_each;
+		if (l == L - 1)
+			node[0] = node[1] = 0xFFFFFFFFu, words_each = 2;
+		else {
+			node[0] = 0xFFu, words_each = 9;
+			for (int i = 1; i < 9; ++i)
+				node[i] = prev;
+		}
+		st = hd_upsert_nodes(p, l, node, words_each, 1, &filled[l]);
+		if (st != HD_OK)
+			return st;
+		if (filled[l] == kNull) {
+			set_error("bucket full while creating filled nodes");
+			return HD_ERR_OVERFLOW;
+		}
+		prev = filled[l];
+	}
+	p->filled = filled;
+	HD_CUDA_TRY(cudaMemcpyAsync(p->edit->filled_dev, p->filled.data(), L * 4, cudaMemcpyHostToDevice, p->stream));
+	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	return HD_OK;
+}
+
+static hd_status read_counters(hd_pool *p, DevCounters &host) {
+	HD_CUDA_TRY(cudaMemcpyAsync(&host, p->edit->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, p->stream));
+	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	return HD_OK;
+}
+
+static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_desc *edits_host, uint32_t n_edits,
+                                 uint32_t *root_out, hd_edit_stats *stats, std::vector<LevelAlloc> &levels,
+                                 hd_edit_desc *&edits_dev, uint32_t *&iota) {
+	const Geometry &g = p->geo;
+	EditScratch *s = p->edit;
+	cudaStream_t st = p->stream;
+	const uint32_t L = g.node_levels;
+
+	HD_CUDA_TRY(amalloc(&edits_dev, n_edits, st));
+	HD_CUDA_TRY(cudaMemcpyAsync(edits_dev, edits_host, sizeof(hd_edit_desc) * n_edits, cudaMemcpyHostToDevice, st));
+	HD_CUDA_TRY(amalloc(&iota, n_edits, st));
+	k_iota<<<grid_for(n_edits), kBlock, 0, st>>>(iota, n_edits);
+	HD_LAUNCH_CHECK();
+	HD_CUDA_TRY(cudaMemsetAsync(s->ctr, 0, sizeof(DevCounters), st));
+
+	levels.resize(L);
+	HD_CUDA_TRY(levels[0].init(1, n_edits, L == 1, st));
+	k_root<<<1, 32, 0, st>>>(g, edits_dev, n_edits, iota, s->filled_dev, root_in, levels[0].v, s->ctr);
+	HD_LAUNCH_CHECK();
+	DevCounters host{};
+	hd_status rs = read_counters(p, host);
+	if (rs != HD_OK)
+		return rs;
+	if (host.next_items == 0) { // the root was not entered at all
+		*root_out = host.root_out;
+		if (stats)
+			memset(stats, 0, sizeof(*stats));
+		return HD_OK;
+	}
+	levels[0].v.n = 1;
+
+	// ---- top-down ----
+	uint32_t deepest = 0;
+	for (uint32_t l = 0; l + 1 < L; ++l) {
+		LevelAlloc &in = levels[l];
+		HD_CUDA_TRY(in.init_up(false));
+		const uint64_t cap = uint64_t(in.v.n) * 8, cap_e = uint64_t(host.next_entries) * 8;
+		if (cap > 0xFFFFFFF0ull || cap_e > 0xFFFFFFF0ull) {
+			set_error("edit batch too large for one pass (%llu items)", (unsigned long long)cap);
+			return HD_ERR_OVERFLOW;
+		}
+		LevelAlloc &out = levels[l + 1];
+		HD_CUDA_TRY(out.init(uint32_t(cap), uint32_t(cap_e), l + 2 == L, st));
+		// reset per-level cursors (stats keep accumulating)
+		HD_CUDA_TRY(cudaMemsetAsync(&s->ctr->next_items, 0, 2 * sizeof(uint32_t), st));
+		k_down<<<grid_for(uint64_t(in.v.n) * 8), kBlock, 0, st>>>(g, l, p->words, edits_dev, s->filled_dev, in.v, out.v,
+		                                                          s->ctr);
+		HD_LAUNCH_CHECK();
+		rs = read_counters(p, host);
+		if (rs != HD_OK)
+			return rs;
+		if (host.error) {
+			set_error("edit scratch overflow at level %u", l + 1);
+			return HD_ERR_OVERFLOW;
+		}
+		out.v.n = host.next_items;
+		if (out.v.n == 0)
+			break;
+		deepest = l + 1;
+	}
+
+	// ---- leaves ----
+	if (deepest == L - 1) {
+		LevelAlloc &lv = levels[L - 1];
+		HD_CUDA_TRY(lv.init_up(true));
+		k_leaf<<<grid_for(uint64_t(lv.v.n) * 32), kBlock, 0, st>>>(g, p->words, edits_dev, lv.v, s->ctr);
+		HD_LAUNCH_CHECK();
+		rs = run_upsert(p, L - 1, lv.v.n, 2, lv.v.cand, lv.v.state, lv.v.winner, lv.v.cur, lv.v.result);
+		if (rs != HD_OK)
+			return rs;
+		k_resolve<<<grid_for(lv.v.n), kBlock, 0, st>>>(lv.v, L >= 2 ? levels[L - 2].v.child_new : nullptr, s->ctr);
+		HD_LAUNCH_CHECK();
+	}
+	// ---- bottom-up ----
+	for (uint32_t l = std::min(deepest, L - 2) + 1; l-- > 0;) {
+		if (L == 1)
+			break;
+		LevelAlloc &lv = levels[l];
+		if (lv.v.n == 0)
+			continue;
+		k_assemble<<<grid_for(lv.v.n), kBlock, 0, st>>>(p->words, lv.v);
+		HD_LAUNCH_CHECK();
+		rs = run_upsert(p, l, lv.v.n, 9, lv.v.cand, lv.v.state, lv.v.winner, lv.v.cur, lv.v.result);
+		if (rs != HD_OK)
+			return rs;
+		k_resolve<<<grid_for(lv.v.n), kBlock, 0, st>>>(lv.v, l ? levels[l - 1].v.child_new : nullptr, s->ctr);
+		HD_LAUNCH_CHECK();
+	}
+	rs = read_counters(p, host);
+	if (rs != HD_OK)
+		return rs;
+	*root_out = host.root_out;
+	if (stats) {
+		stats->visited_nodes = 0;
+		for (uint32_t l = 0; l + 1 < L; ++l)
+			stats->visited_nodes += levels[l].v.n;
+		stats->visited_leaves = levels[L - 1].v.n;
+		stats->upserts = host.stats[2];
+		stats->appended_nodes = host.stats[3];
+		stats->appended_words = host.stats[4];
+		stats->overflow_count = host.stats[5];
+		stats->in_range_voxels = 0;
+		stats->scan_words = host.stats[7];
+	}
+	return HD_OK;
+}
+
+} // namespace hd
+
+using namespace hd;
+
+extern "C" {
+
+hd_status hd_edit_batch(hd_pool *p, uint32_t root_in, const hd_edit_desc *edits, uint32_t n, uint32_t *root_out,
+                        hd_edit_stats *stats) {
+	if (!p || !root_out || (!edits && n))
+		return HD_ERR_INVALID;
+	*root_out = root_in;
+	if (stats)
+		memset(stats, 0, sizeof(*stats));
+	if (n == 0)
+		return HD_OK;
+	for (uint32_t i = 0; i < n; ++i)
+		if (edits[i].kind > HD_EDIT_TERRAIN_FILL) {
+			set_error("unknown edit kind %u", edits[i].kind);
+			return HD_ERR_INVALID;
+		}
+	HD_CUDA_TRY(cudaSetDevice(p->device));
+	hd_status st = scratch_init(p);
+	if (st == HD_OK)
+		st = ensure_filled(p); // NodePool.hpp:408
+	if (st != HD_OK)
+		return st;
+	std::vector<LevelAlloc> levels;
+	hd_edit_desc *edits_dev = nullptr;
+	uint32_t *iota = nullptr;
+	st = edit_batch_impl(p, root_in, edits, n, root_out, stats, levels, edits_dev, iota);
+	for (auto &l : levels)
+		l.release();
+	if (edits_dev)
+		cudaFreeAsync(edits_dev, p->stream);
+	if (iota)
+		cudaFreeAsync(iota, p->stream);
+	cudaStreamSynchronize(p->stream);
+	if (st != HD_OK)
+		*root_out = root_in;
+	return st;
+}
+
+hd_status hd_upsert_nodes(hd_pool *p, uint32_t level, const uint32_t *nodes, uint32_t words_each, uint32_t n,
+                          uint32_t *out_ptrs) {
+	if (!p || !nodes || !out_ptrs || level >= p->geo.node_levels || words_each < 2 || words_each > 9)
+		return HD_ERR_INVALID;
+	const bool is_leaf = level == p->geo.node_levels - 1;
+	if (is_leaf && words_each != 2)
+		return HD_ERR_INVALID;
+	if (n == 0)
+		return HD_OK;
+	if (!is_leaf)
+		for (uint32_t i = 0; i < n; ++i) {
+			const uint32_t m = nodes[size_t(i) * words_each];
+			if (m == 0 || m > 0xFFu || 1u + uint32_t(__builtin_popcount(m)) > words_each)
+				return HD_ERR_INVALID;
+		}
+	HD_CUDA_TRY(cudaSetDevice(p->device));
+	hd_status st = scratch_init(p);
+	if (st != HD_OK)
+		return st;
+	cudaStream_t s = p->stream;
+	uint32_t *cand = nullptr, *winner = nullptr, *result = nullptr;
+	uint8_t *state = nullptr;
+	HD_CUDA_TRY(amalloc(&cand, uint64_t(n) * words_each, s));
+	HD_CUDA_TRY(amalloc(&winner, n, s));
+	HD_CUDA_TRY(amalloc(&result, n, s));
+	HD_CUDA_TRY(amalloc(&state, n, s));
+	HD_CUDA_TRY(cudaMemcpyAsync(cand, nodes, uint64_t(n) * words_each * 4, cudaMemcpyHostToDevice, s));
+	HD_CUDA_TRY(cudaMemsetAsync(result, 0xFF, uint64_t(n) * 4, s));
+	k_fill_u8<<<grid_for(n), kBlock, 0, s>>>(state, n, 1);
+	HD_LAUNCH_CHECK();
+	st = run_upsert(p, level, n, words_each, cand, state, winner, nullptr, result);
+	if (st == HD_OK) {
+		k_resolve_flat<<<grid_for(n), kBlock, 0, s>>>(n, state, winner, result);
+		hd::g_launches.fetch_add(1);
+		HD_CUDA_TRY(cudaMemcpyAsync(out_ptrs, result, uint64_t(n) * 4, cudaMemcpyDeviceToHost, s));
+	}
+	cudaFreeAsync(cand, s), cudaFreeAsync(winner, s), cudaFreeAsync(result, s), cudaFreeAsync(state, s);
+	HD_CUDA_TRY(cudaStreamSynchronize(s));
+	return st;
+}
+
+hd_status hd_pool_used_words(hd_pool *p, uint64_t *out) {
+	if (!p || !out)
+		return HD_ERR_INVALID;
+	std::vector<uint32_t> bw(p->geo.total_buckets);
+	hd_status s = hd_pool_read_bucket_words(p, 0, bw.data(), p->geo.total_buckets);
+	if (s != HD_OK)
+		return s;
+	uint64_t sum = 0;
+	for (uint32_t v : bw)
+		sum += v;
+	*out = sum;
+	return HD_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,161 @@
+// editors.cuh — device predicates selected by hd_edit_desc::kind.
+//
+// Semantics follow the reference's editor structs (src/main.cpp:32-150): EditNode classifies an octree node by
+// its integer voxel-space bounds (NodeCoord::GetLower/UpperBoundAtLevel, include/hashdag/NodeCoord.hpp:86-93),
+// EditVoxel decides one voxel.  All arithmetic is exact integer (i64/u64), so CPU and GPU agree bit for bit.
+// The terrain generator is the synthetic scene of SURVEY.md §8d cfg2 (normative definition in DESIGN.md).
+#pragma once
+#include "common.cuh"
+
+namespace hd {
+
+enum EditType : uint32_t { kNotAffected = 0, kProceed = 1, kFill = 2, kClear = 3 }; // include/hashdag/Editor.hpp:18
+
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+	h ^= h >> 16;
+	h *= 0x85ebca6bu;
+	h ^= h >> 13;
+	h *= 0xc2b2ae35u;
+	h ^= h >> 16;
+	return h;
+}
+
+struct TerrainOctave {
+	uint32_t cell_bits, amp, hseed;
+};
+
+__device__ __forceinline__ uint32_t terrain_lattice(uint32_t hseed, uint32_t ix, uint32_t iz) {
+	return fmix32(fmix32(hseed ^ (ix * 0x85EBCA6Bu)) ^ (iz * 0xC2B2AE35u)) >> 16;
+}
+__device__ __forceinline__ uint32_t terrain_bilerp(uint32_t v00, uint32_t v10, uint32_t v01, uint32_t v11, uint32_t fx,
+                                                   uint32_t fz, uint32_t c) {
+	const uint64_t S = 1ull << c;
+	const uint64_t a = uint64_t(v00) * (S - fx) + uint64_t(v10) * fx;
+	const uint64_t b = uint64_t(v01) * (S - fx) + uint64_t(v11) * fx;
+	return uint32_t((a * (S - fz) + b * fz) >> (2 * c));
+}
+__device__ __forceinline__ bool terrain_octave(const hd_edit_desc &d, uint32_t o, TerrainOctave &out) {
+	if (o >= d.p0[2] || d.p0[1] < 2 * o)
+		return false;
+	out.cell_bits = d.p0[1] - 2 * o;
+	out.amp = d.p1[0] >> (2 * o);
+	out.hseed = fmix32(d.aux + o * 0x9E3779B9u);
+	return true;
+}
+
+__device__ inline uint32_t terrain_height(const hd_edit_desc &d, uint32_t x, uint32_t z) {
+	uint32_t h = d.p0[0];
+	TerrainOctave oc;
+	for (uint32_t o = 0; terrain_octave(d, o, oc); ++o) {
+		const uint32_t c = oc.cell_bits, ix = x >> c, iz = z >> c, m = (1u << c) - 1u;
+		const uint32_t r = terrain_bilerp(terrain_lattice(oc.hseed, ix, iz), terrain_lattice(oc.hseed, ix + 1, iz),
+		                                  terrain_lattice(oc.hseed, ix, iz + 1), terrain_lattice(oc.hseed, ix + 1, iz + 1),
+		                                  x & m, z & m, c);
+		h += uint32_t((uint64_t(r) * oc.amp) >> 16);
+	}
+	return h;
+}
+
+// conservative height range over the footprint [lx,lx+2^k) x [lz,lz+2^k)
+__device__ inline void terrain_bounds(const hd_edit_desc &d, uint32_t lx, uint32_t lz, uint32_t k, uint32_t &hmin,
+                                      uint32_t &hmax) {
+	hmin = hmax = d.p0[0];
+	TerrainOctave oc;
+	for (uint32_t o = 0; terrain_octave(d, o, oc); ++o) {
+		const uint32_t c = oc.cell_bits;
+		uint32_t rmin, rmax;
+		if (k <= c) {
+			const uint32_t ix = lx >> c, iz = lz >> c, m = (1u << c) - 1u;
+			const uint32_t v00 = terrain_lattice(oc.hseed, ix, iz), v10 = terrain_lattice(oc.hseed, ix + 1, iz),
+			               v01 = terrain_lattice(oc.hseed, ix, iz + 1), v11 = terrain_lattice(oc.hseed, ix + 1, iz + 1);
+			const uint32_t fx0 = lx & m, fz0 = lz & m, fx1 = fx0 + (1u << k), fz1 = fz0 + (1u << k);
+			const uint32_t r0 = terrain_bilerp(v00, v10, v01, v11, fx0, fz0, c),
+			               r1 = terrain_bilerp(v00, v10, v01, v11, fx1, fz0, c),
+			               r2 = terrain_bilerp(v00, v10, v01, v11, fx0, fz1, c),
+			               r3 = terrain_bilerp(v00, v10, v01, v11, fx1, fz1, c);
+			rmin = min(min(r0, r1), min(r2, r3));
+			rmax = max(max(r0, r1), max(r2, r3));
+		} else if (k - c <= 2) {
+			const uint32_t n = 1u << (k - c), ix = lx >> c, iz = lz >> c;
+			rmin = 0xFFFFu, rmax = 0u;
+			for (uint32_t j = 0; j <= n; ++j)
+				for (uint32_t i = 0; i <= n; ++i) {
+					const uint32_t v = terrain_lattice(oc.hseed, ix + i, iz + j);
+					rmin = min(rmin, v), rmax = max(rmax, v);
+				}
+		} else {
+			rmin = 0u, rmax = 0xFFFFu;
+		}
+		hmin += uint32_t((uint64_t(rmin) * oc.amp) >> 16);
+		hmax += uint32_t((uint64_t(rmax) * oc.amp) >> 16);
+	}
+}
+
+// EditNode: node at `level` with integer position (x,y,z); bits = voxel_level - level.
+__device__ inline EditType edit_node(const hd_edit_desc &d, uint32_t bits, uint32_t x, uint32_t y, uint32_t z) {
+	const uint32_t lb[3] = {x << bits, y << bits, z << bits};
+	const uint32_t ub[3] = {(x + 1u) << bits, (y + 1u) << bits, (z + 1u) << bits};
+	switch (d.kind) {
+	case HD_EDIT_AABB_FILL: { // main.cpp:35-46
+		bool outside = false, inside = true;
+#pragma unroll
+		for (int i = 0; i < 3; ++i) {
+			outside |= ub[i] <= d.p0[i] || lb[i] >= d.p1[i];
+			inside &= lb[i] >= d.p0[i] && ub[i] <= d.p1[i];
+		}
+		return outside ? kNotAffected : (inside ? kFill : kProceed);
+	}
+	case HD_EDIT_SPHERE_FILL:
+	case HD_EDIT_SPHERE_DIG: { // main.cpp:77-106
+		uint64_t max_n2 = 0, min_n2 = 0;
+#pragma unroll
+		for (int i = 0; i < 3; ++i) {
+			const long long lo = (long long)lb[i] - (long long)d.p0[i], hi = (long long)ub[i] - (long long)d.p0[i];
+			const uint64_t lo2 = uint64_t(lo * lo), hi2 = uint64_t(hi * hi);
+			max_n2 += lo2 > hi2 ? lo2 : hi2;
+			if (lo > 0)
+				min_n2 += lo2;
+			if (hi < 0)
+				min_n2 += hi2;
+		}
+		if (max_n2 <= d.r2)
+			return d.kind == HD_EDIT_SPHERE_DIG ? kClear : kFill;
+		return min_n2 > d.r2 ? kNotAffected : kProceed;
+	}
+	case HD_EDIT_TERRAIN_FILL: {
+		uint32_t hmin, hmax;
+		terrain_bounds(d, lb[0], lb[2], bits, hmin, hmax);
+		if (ub[1] <= hmin)
+			return kFill;
+		if (lb[1] >= hmax)
+			return kNotAffected;
+		return kProceed;
+	}
+	}
+	return kNotAffected;
+}
+
+// VoxelInRange (main.cpp:57-59,127-132)
+__device__ inline bool voxel_in_range(const hd_edit_desc &d, uint32_t x, uint32_t y, uint32_t z) {
+	switch (d.kind) {
+	case HD_EDIT_AABB_FILL:
+		return x >= d.p0[0] && y >= d.p0[1] && z >= d.p0[2] && x < d.p1[0] && y < d.p1[1] && z < d.p1[2];
+	case HD_EDIT_SPHERE_FILL:
+	case HD_EDIT_SPHERE_DIG: {
+		const long long dx = (long long)x - (long long)d.p0[0], dy = (long long)y - (long long)d.p0[1],
+		                dz = (long long)z - (long long)d.p0[2];
+		return uint64_t(dx * dx + dy * dy + dz * dz) <= d.r2;
+	}
+	case HD_EDIT_TERRAIN_FILL:
+		return y < terrain_height(d, x, z);
+	}
+	return false;
+}
+
+// EditVoxel (main.cpp:60-63,133-142)
+__device__ __forceinline__ bool edit_voxel(const hd_edit_desc &d, uint32_t x, uint32_t y, uint32_t z, bool voxel) {
+	const bool in = voxel_in_range(d, x, y, z);
+	return d.kind == HD_EDIT_SPHERE_DIG ? (voxel && !in) : (voxel || in);
+}
+
+} // namespace hd

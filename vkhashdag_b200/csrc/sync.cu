@@ -1,0 +1,200 @@
+// sync.cu — dirty-range tracking and replica synchronisation (multi-GPU: pool replicated).
+//
+// Replaces DAGNodePool::Flush (src/DAGNodePool.cpp:56-85) and its per-page m_page_write_ranges bookkeeping
+// (src/DAGNodePool.hpp:44-46,62-69).  Buckets are append-only between GCs, so "what changed since the last
+// sync" is exactly [bucket_synced[b], bucket_words[b]) for every bucket: no write log is needed.  The editing
+// rank packs those runs into ONE staging buffer, the caller broadcasts it (one NCCL broadcast over NVLink),
+// replicas scatter it and publish the root last.
+//
+// Staging layout (u32 words): [n_ranges][payload_words][root][0] then n_ranges x {word_offset, word_count,
+// payload_offset} then the payload.
+#include "common.cuh"
+
+namespace hd {
+
+constexpr uint32_t kHeaderWords = 4;
+
+__global__ void k_dirty_scan(const uint32_t *__restrict__ cur, const uint32_t *__restrict__ synced, uint32_t n_buckets,
+                             uint32_t bucket_shift, uint32_t *header, uint32_t *ranges, uint32_t capacity) {
+	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n_buckets)
+		return;
+	const uint32_t c = cur[b], s = synced[b];
+	if (c <= s)
+		return;
+	const uint32_t idx = atomicAdd(&header[0], 1u);
+	const uint32_t poff = atomicAdd(&header[1], c - s);
+	if (ranges && idx < capacity) {
+		ranges[idx * 3 + 0] = (b << bucket_shift) + s;
+		ranges[idx * 3 + 1] = c - s;
+		ranges[idx * 3 + 2] = poff;
+	}
+}
+
+// one CTA per range at a time (grid-stride); n_ranges is read from the device header
+__global__ void k_dirty_gather(const uint32_t *__restrict__ words, const uint32_t *__restrict__ header,
+                               const uint32_t *__restrict__ ranges, uint32_t *payload) {
+	const uint32_t n = header[0];
+	for (uint32_t r = blockIdx.x; r < n; r += gridDim.x) {
+		const uint32_t off = ranges[r * 3], cnt = ranges[r * 3 + 1], poff = ranges[r * 3 + 2];
+		for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
+			payload[poff + i] = words[off + i];
+	}
+}
+
+__global__ void k_dirty_scatter(uint32_t *words, uint32_t *bucket_words, uint32_t *bucket_synced, uint32_t bucket_shift,
+                                const uint32_t *__restrict__ header, const uint32_t *__restrict__ ranges,
+                                const uint32_t *__restrict__ payload) {
+	const uint32_t n = header[0];
+	for (uint32_t r = blockIdx.x; r < n; r += gridDim.x) {
+		const uint32_t off = ranges[r * 3], cnt = ranges[r * 3 + 1], poff = ranges[r * 3 + 2];
+		for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
+			words[off + i] = payload[poff + i];
+		if (threadIdx.x == 0) {
+			const uint32_t bucket = off >> bucket_shift;
+			const uint32_t end = (off & ((1u << bucket_shift) - 1u)) + cnt;
+			bucket_words[bucket] = end;
+			bucket_synced[bucket] = end;
+		}
+	}
+}
+
+static hd_status ensure_dirty_scratch(hd_pool *p, uint64_t bytes) {
+	if (p->dirty_scratch_bytes >= bytes)
+		return HD_OK;
+	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	cudaFree(p->dirty_scratch);
+	p->dirty_scratch = nullptr, p->dirty_scratch_bytes = 0;
+	HD_CUDA_TRY(cudaMalloc(&p->dirty_scratch, bytes));
+	p->dirty_scratch_bytes = bytes;
+	return HD_OK;
+}
+
+static hd_status scan_counts(hd_pool *p, uint32_t host_header[kHeaderWords]) {
+	hd_status s = ensure_dirty_scratch(p, kHeaderWords * 4);
+	if (s != HD_OK)
+		return s;
+	HD_CUDA_TRY(cudaMemsetAsync(p->dirty_scratch, 0, kHeaderWords * 4, p->stream));
+	const uint32_t nb = p->geo.total_buckets;
+	k_dirty_scan<<<(nb + 255) / 256, 256, 0, p->stream>>>(p->bucket_words, p->bucket_synced, nb, p->geo.bucket_shift(),
+	                                                      p->dirty_scratch, nullptr, 0);
+	HD_LAUNCH_CHECK();
+	HD_CUDA_TRY(cudaMemcpyAsync(host_header, p->dirty_scratch, kHeaderWords * 4, cudaMemcpyDeviceToHost, p->stream));
+	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	return HD_OK;
+}
+
+} // namespace hd
+
+using namespace hd;
+
+extern "C" {
+
+hd_status hd_dirty_count(hd_pool *p, uint32_t *n_ranges, uint64_t *packed_bytes) {
+	if (!p)
+		return HD_ERR_INVALID;
+	HD_CUDA_TRY(cudaSetDevice(p->device));
+	uint32_t h[kHeaderWords];
+	hd_status s = scan_counts(p, h);
+	if (s != HD_OK)
+		return s;
+	if (n_ranges)
+		*n_ranges = h[0];
+	if (packed_bytes)
+		*packed_bytes = (uint64_t(kHeaderWords) + uint64_t(h[0]) * 3 + h[1]) * 4;
+	return HD_OK;
+}
+
+hd_status hd_dirty_ranges(hd_pool *p, hd_dirty_range *out, uint32_t capacity, uint32_t *n_out) {
+	if (!p || !n_out || (!out && capacity))
+		return HD_ERR_INVALID;
+	HD_CUDA_TRY(cudaSetDevice(p->device));
+	uint32_t h[kHeaderWords];
+	hd_status s = scan_counts(p, h);
+	if (s != HD_OK)
+		return s;
+	*n_out = h[0];
+	if (h[0] == 0 || capacity == 0)
+		return HD_OK;
+	s = ensure_dirty_scratch(p, (kHeaderWords + uint64_t(h[0]) * 3) * 4);
+	if (s != HD_OK)
+		return s;
+	HD_CUDA_TRY(cudaMemsetAsync(p->dirty_scratch, 0, kHeaderWords * 4, p->stream));
+	const uint32_t nb = p->geo.total_buckets;
+	k_dirty_scan<<<(nb + 255) / 256, 256, 0, p->stream>>>(p->bucket_words, p->bucket_synced, nb, p->geo.bucket_shift(),
+	                                                      p->dirty_scratch, p->dirty_scratch + kHeaderWords, h[0]);
+	HD_LAUNCH_CHECK();
+	std::vector<uint32_t> tri(size_t(h[0]) * 3);
+	HD_CUDA_TRY(cudaMemcpyAsync(tri.data(), p->dirty_scratch + kHeaderWords, tri.size() * 4, cudaMemcpyDeviceToHost,
+	                            p->stream));
+	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	for (uint32_t i = 0; i < h[0] && i < capacity; ++i)
+		out[i] = hd_dirty_range{tri[i * 3], tri[i * 3 + 1]};
+	return HD_OK;
+}
+
+hd_status hd_dirty_pack_dev(hd_pool *p, void *staging_dev, uint64_t capacity_bytes, uint64_t *packed_bytes) {
+	if (!p || !staging_dev || !packed_bytes || capacity_bytes < kHeaderWords * 4)
+		return HD_ERR_INVALID;
+	HD_CUDA_TRY(cudaSetDevice(p->device));
+	uint32_t h[kHeaderWords];
+	hd_status s = scan_counts(p, h);
+	if (s != HD_OK)
+		return s;
+	const uint64_t need = (uint64_t(kHeaderWords) + uint64_t(h[0]) * 3 + h[1]) * 4;
+	*packed_bytes = need;
+	if (need > capacity_bytes) {
+		set_error("staging buffer too small: need %llu bytes", (unsigned long long)need);
+		return HD_ERR_OVERFLOW;
+	}
+	uint32_t *stg = static_cast<uint32_t *>(staging_dev);
+	uint32_t *ranges = stg + kHeaderWords, *payload = ranges + size_t(h[0]) * 3;
+	HD_CUDA_TRY(cudaMemsetAsync(stg, 0, kHeaderWords * 4, p->stream));
+	const uint32_t nb = p->geo.total_buckets;
+	k_dirty_scan<<<(nb + 255) / 256, 256, 0, p->stream>>>(p->bucket_words, p->bucket_synced, nb, p->geo.bucket_shift(), stg,
+	                                                      ranges, h[0]);
+	HD_LAUNCH_CHECK();
+	if (h[0]) {
+		k_dirty_gather<<<std::min<uint32_t>(h[0], 148u * 8u), 256, 0, p->stream>>>(p->words, stg, ranges, payload);
+		HD_LAUNCH_CHECK();
+	}
+	const uint32_t root = p->root;
+	HD_CUDA_TRY(cudaMemcpyAsync(stg + 2, &root, 4, cudaMemcpyHostToDevice, p->stream));
+	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	return HD_OK;
+}
+
+hd_status hd_dirty_apply_dev(hd_pool *p, const void *staging_dev, uint64_t packed_bytes) {
+	if (!p || !staging_dev || packed_bytes < kHeaderWords * 4)
+		return HD_ERR_INVALID;
+	HD_CUDA_TRY(cudaSetDevice(p->device));
+	const uint32_t *stg = static_cast<const uint32_t *>(staging_dev);
+	uint32_t h[kHeaderWords];
+	HD_CUDA_TRY(cudaMemcpyAsync(h, stg, sizeof(h), cudaMemcpyDeviceToHost, p->stream));
+	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	if ((uint64_t(kHeaderWords) + uint64_t(h[0]) * 3 + h[1]) * 4 > packed_bytes) {
+		set_error("staging buffer truncated");
+		return HD_ERR_INVALID;
+	}
+	if (h[0]) {
+		const uint32_t *ranges = stg + kHeaderWords, *payload = ranges + size_t(h[0]) * 3;
+		k_dirty_scatter<<<std::min<uint32_t>(h[0], 148u * 8u), 256, 0, p->stream>>>(
+		    p->words, p->bucket_words, p->bucket_synced, p->geo.bucket_shift(), stg, ranges, payload);
+		HD_LAUNCH_CHECK();
+	}
+	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	p->root = h[2]; // publish the root last (src/main.cpp:281-296 ordering contract)
+	return HD_OK;
+}
+
+hd_status hd_dirty_reset(hd_pool *p) {
+	if (!p)
+		return HD_ERR_INVALID;
+	HD_CUDA_TRY(cudaSetDevice(p->device));
+	HD_CUDA_TRY(cudaMemcpyAsync(p->bucket_synced, p->bucket_words, size_t(p->geo.total_buckets) * 4,
+	                            cudaMemcpyDeviceToDevice, p->stream));
+	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	return HD_OK;
+}
+
+} // extern "C"
