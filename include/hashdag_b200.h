@@ -55,7 +55,8 @@ typedef struct hd_default_config {
  *  SPHERE_FILL  : p0 = center, r2                                  main.cpp:72-150 (EditMode::kFill)
  *  SPHERE_DIG   : p0 = center, r2                                  (EditMode::kDig)
  *  TERRAIN_FILL : integer value-noise height field (synthetic scene generator):
- *                 aux = seed, p0 = {base_height, first_cell_bits, octaves}, p1 = {first_amplitude,0,0};
+ *                 aux = seed, p0 = {base_height, first_cell_bits, octaves}, p1 = {first_amplitude, extent_bits, 0}
+ *                 (extent_bits != 0: only columns x,z < 2^extent_bits carry terrain — a patch of a larger world);
  *                 octave o has lattice cell 2^(first_cell_bits-2o) voxels and amplitude first_amplitude>>(2o);
  *                 voxel (x,y,z) becomes solid iff y < height(x,z).
  */
@@ -109,6 +110,8 @@ typedef struct hd_trace_outputs {
 	uint32_t *rgba8;       /* shaded frame, trace.frag:395-401 converted to UNORM8 (r low byte, a = 255) */
 	hd_hit_record *hits;   /* parity records */
 	uint32_t *iters;       /* loop iterations, trace.frag:129 */
+	uint32_t *fetches;     /* 32-bit node/colour words the reference algorithm reads for this ray (F of SURVEY §8d);
+	                          requesting it selects an instrumented kernel variant — not for timed runs */
 } hd_trace_outputs;
 
 /* Screen-tile sharding of one frame over `world` GPUs: tile t = ty*tiles_x+tx (tile_w x tile_h px)

@@ -223,7 +223,7 @@ struct EditorCtx {
 	terrain::Params tp;
 	mutable HeightCache hc;
 	explicit EditorCtx(const hd_edit_desc &desc, uint32_t vl) : d(desc), voxel_level(vl) {
-		tp = {d.aux, d.p0[0], d.p0[1], d.p0[2], d.p1[0]};
+		tp = terrain::from_desc(d.aux, d.p0, d.p1);
 	}
 
 	uint32_t terrain_height(uint32_t x, uint32_t z) const {
@@ -263,12 +263,15 @@ struct EditorCtx {
 			return min_n2 > d.r2 ? kNotAffected : kProceed;
 		}
 		case HD_EDIT_TERRAIN_FILL: {
+			const int ext = terrain::extent_class(tp, b.lb[0], b.lb[2], voxel_level - level);
+			if (ext == 0)
+				return kNotAffected;
 			uint32_t hmin, hmax;
 			terrain::height_bounds(tp, b.lb[0], b.lb[2], voxel_level - level, hmin, hmax);
-			if (b.ub[1] <= hmin)
-				return kFill;
 			if (b.lb[1] >= hmax)
 				return kNotAffected;
+			if (ext == 2 && b.ub[1] <= hmin)
+				return kFill;
 			return kProceed;
 		}
 		}
@@ -287,7 +290,7 @@ struct EditorCtx {
 			return uint64_t(dx * dx + dy * dy + dz * dz) <= d.r2;
 		}
 		case HD_EDIT_TERRAIN_FILL:
-			return v[1] < terrain_height(v[0], v[2]);
+			return terrain::in_extent(tp, v[0], v[2]) && v[1] < terrain_height(v[0], v[2]);
 		}
 		return false;
 	}
@@ -907,10 +910,11 @@ uint64_t orc_in_range_voxels(const hd_edit_desc *d, uint32_t voxel_level) {
 		return total;
 	}
 	case HD_EDIT_TERRAIN_FILL: {
-		terrain::Params tp{d->aux, d->p0[0], d->p0[1], d->p0[2], d->p1[0]};
+		terrain::Params tp = terrain::from_desc(d->aux, d->p0, d->p1);
 		uint64_t total = 0;
-		for (uint64_t z = 0; z < res; ++z)
-			for (uint64_t x = 0; x < res; ++x)
+		const uint64_t ext = tp.extent_bits ? std::min<uint64_t>(res, 1ull << tp.extent_bits) : res;
+		for (uint64_t z = 0; z < ext; ++z)
+			for (uint64_t x = 0; x < ext; ++x)
 				total += std::min<uint64_t>(terrain::height(tp, uint32_t(x), uint32_t(z)), res);
 		return total;
 	}
@@ -918,7 +922,7 @@ uint64_t orc_in_range_voxels(const hd_edit_desc *d, uint32_t voxel_level) {
 	return 0;
 }
 uint32_t orc_terrain_height(const hd_edit_desc *d, uint32_t x, uint32_t z) {
-	terrain::Params tp{d->aux, d->p0[0], d->p0[1], d->p0[2], d->p1[0]};
+	terrain::Params tp = terrain::from_desc(d->aux, d->p0, d->p1);
 	return terrain::height(tp, x, z);
 }
 

@@ -165,12 +165,15 @@ struct TerrainEd { // synthetic scene generator, oracle/terrain.h
 	terrain::Params tp;
 	EditType EditNode(const Cfg &config, const Coord &coord, NPtr) const {
 		BoxU b = bounds(config, coord);
+		const int ext = terrain::extent_class(tp, b.lb.x, b.lb.z, config.GetVoxelLevel() - coord.level);
+		if (ext == 0)
+			return EditType::kNotAffected;
 		uint32_t hmin, hmax;
 		terrain::height_bounds(tp, b.lb.x, b.lb.z, config.GetVoxelLevel() - coord.level, hmin, hmax);
-		if (b.ub.y <= hmin)
-			return EditType::kFill;
 		if (b.lb.y >= hmax)
 			return EditType::kNotAffected;
+		if (ext == 2 && b.ub.y <= hmin)
+			return EditType::kFill;
 		return EditType::kProceed;
 	}
 	bool EditVoxel(const Cfg &, const Coord &c, bool voxel) const {
@@ -190,7 +193,7 @@ struct TerrainEd { // synthetic scene generator, oracle/terrain.h
 			h = terrain::height(tp, c.pos.x, c.pos.z);
 			cache.valid |= 1u << s, cache.x[s] = c.pos.x, cache.z[s] = c.pos.z, cache.h[s] = h;
 		}
-		return voxel || c.pos.y < h;
+		return voxel || (terrain::in_extent(tp, c.pos.x, c.pos.z) && c.pos.y < h);
 	}
 };
 
@@ -424,7 +427,7 @@ uint32_t ref_edit(ref_pool *p, uint32_t root, const hd_edit_desc *d, uint32_t th
 	case HD_EDIT_SPHERE_DIG:
 		return run_stateless(pool, root, SphereEd<Mode::kDig>{a, d->r2, {}}, threads, max_task_level);
 	case HD_EDIT_TERRAIN_FILL:
-		return run_stateless(pool, root, TerrainEd{{d->aux, d->p0[0], d->p0[1], d->p0[2], d->p1[0]}}, threads,
+		return run_stateless(pool, root, TerrainEd{terrain::from_desc(d->aux, d->p0, d->p1)}, threads,
 		                     max_task_level);
 	}
 	return root;

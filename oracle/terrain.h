@@ -9,6 +9,7 @@
 //   octave o: cell = 2^c, c = first_cell_bits - 2o, amplitude a = first_amplitude >> 2o
 //             r(x,z) = bilinear integer interpolation of the 4 lattice values, in [0,65535]
 //   height(x,z) = base + sum_o (r_o(x,z) * a_o) >> 16 ;  voxel solid iff y < height(x,z)
+//   optional patch: with extent_bits = e != 0 only columns x,z < 2^e carry terrain (rest of the world stays empty)
 #pragma once
 #include <cstdint>
 
@@ -16,7 +17,24 @@ namespace terrain {
 
 struct Params {
 	uint32_t seed, base, first_cell_bits, octaves, first_amplitude;
+	uint32_t extent_bits = 0; // != 0: the terrain only exists for x,z < 2^extent_bits (a patch of a larger world)
 };
+
+inline Params from_desc(uint32_t aux, const uint32_t p0[3], const uint32_t p1[3]) {
+	return Params{aux, p0[0], p0[1], p0[2], p1[0], p1[1]};
+}
+// footprint [lx,lx+2^k) x [lz,lz+2^k): 0 = outside the patch, 1 = partly inside, 2 = fully inside
+inline int extent_class(const Params &p, uint32_t lx, uint32_t lz, uint32_t k) {
+	if (p.extent_bits == 0)
+		return 2;
+	const uint64_t e = 1ull << p.extent_bits, s = 1ull << k;
+	if (lx >= e || lz >= e)
+		return 0;
+	return (lx + s <= e && lz + s <= e) ? 2 : 1;
+}
+inline bool in_extent(const Params &p, uint32_t x, uint32_t z) {
+	return p.extent_bits == 0 || ((x >> p.extent_bits) == 0 && (z >> p.extent_bits) == 0);
+}
 
 inline uint32_t fmix32(uint32_t h) {
 	h ^= h >> 16;

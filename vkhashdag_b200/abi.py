@@ -91,14 +91,17 @@ def sphere(center, r2, dig=False):
     return d
 
 
-def terrain(voxel_level, seed=0x5EED, octaves=4):
-    """The synthetic noise terrain of SURVEY §8d cfg2 scaled to the resolution (oracle/terrain.h)."""
-    res = 1 << voxel_level
+def terrain(voxel_level, seed=0x5EED, octaves=4, amp_div=8, extent_bits=0):
+    """The synthetic noise terrain of SURVEY §8d cfg2 (oracle/terrain.h).  With E = extent (the whole
+    world, or a 2^extent_bits patch of it): base height E/4, octave o has lattice cell E/4^(o+1) and amplitude
+    E/(amp_div*4^o)."""
+    bits = extent_bits if extent_bits else voxel_level
+    ext = 1 << bits
     d = HdEditDesc()
     d.kind = EDIT_TERRAIN_FILL
     d.aux = seed
-    d.p0[:] = (res // 4, voxel_level - 2, octaves)
-    d.p1[:] = (res // 4, 0, 0)
+    d.p0[:] = (ext // 4, bits - 2, octaves)
+    d.p1[:] = (ext // amp_div, extent_bits, 0)
     return d
 
 
@@ -109,11 +112,11 @@ def edit_array(edits):
     return arr
 
 
-def random_spheres(n, voxel_level, seed=1234, rmin=16, rmax=256, y_lo=None, y_hi=None):
-    """xorshift32 centres in the terrain band, radius uniform, alternating fill/dig."""
-    res = 1 << voxel_level
+def random_spheres(n, voxel_level, seed=1234, rmin=16, rmax=256, y_lo=None, y_hi=None, extent_bits=0):
+    """xorshift32 centres in the terrain band (of the patch), radius uniform, alternating fill/dig."""
+    res = 1 << (extent_bits if extent_bits else voxel_level)
     y_lo = res // 4 if y_lo is None else y_lo
-    y_hi = res // 4 + res // 3 if y_hi is None else y_hi
+    y_hi = res // 4 + res // 6 if y_hi is None else y_hi
     s = seed & 0xFFFFFFFF
 
     def nxt():

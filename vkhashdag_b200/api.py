@@ -32,7 +32,7 @@ class HdEditStats(C.Structure):
 
 
 class HdTraceOutputs(C.Structure):
-    _fields_ = [("rgba8", C.c_void_p), ("hits", C.c_void_p), ("iters", C.c_void_p)]
+    _fields_ = [("rgba8", C.c_void_p), ("hits", C.c_void_p), ("iters", C.c_void_p), ("fetches", C.c_void_p)]
 
 
 class HdTileShard(C.Structure):
@@ -149,8 +149,8 @@ class SphereEditor:
 
 
 class TerrainEditor:
-    def __init__(self, voxel_level, seed=0x5EED, octaves=4):
-        self.desc = abi.terrain(voxel_level, seed, octaves)
+    def __init__(self, voxel_level, seed=0x5EED, octaves=4, amp_div=8, extent_bits=0):
+        self.desc = abi.terrain(voxel_level, seed, octaves, amp_div, extent_bits)
 
 
 def _desc(e):
@@ -293,18 +293,21 @@ class DAGNodePool:
             res["hits"] = np.zeros(shape, HIT_DTYPE)
         if "iters" in want and "iters" not in res:
             res["iters"] = np.zeros(shape, np.uint32)
+        if "fetches" in want and "fetches" not in res:
+            res["fetches"] = np.zeros(shape, np.uint32)
         o = HdTraceOutputs(res["rgba8"].ctypes.data if "rgba8" in want else None,
                            res["hits"].ctypes.data if "hits" in want else None,
-                           res["iters"].ctypes.data if "iters" in want else None)
+                           res["iters"].ctypes.data if "iters" in want else None,
+                           res["fetches"].ctypes.data if "fetches" in want else None)
         if shard is None:
             _check(self._L.hd_trace(self._h, C.byref(params), C.byref(o)))
         else:
             _check(self._L.hd_trace_tiles(self._h, C.byref(params), C.byref(shard), C.byref(o)))
         return res
 
-    def TraceDev(self, params, rgba8=0, hits=0, iters=0, shard=None):
+    def TraceDev(self, params, rgba8=0, hits=0, iters=0, fetches=0, shard=None):
         """Enqueue one frame with DEVICE output pointers (ints, e.g. torch.Tensor.data_ptr()); no synchronisation."""
-        o = HdTraceOutputs(rgba8 or None, hits or None, iters or None)
+        o = HdTraceOutputs(rgba8 or None, hits or None, iters or None, fetches or None)
         if shard is None:
             _check(self._L.hd_trace_dev(self._h, C.byref(params), C.byref(o)))
         else:

@@ -79,7 +79,7 @@ struct hd_pool {
 	std::vector<uint32_t> filled; // m_filled_node_pointers (NodePool.hpp:54)
 
 	// trace staging (device) for the host-pointer entry points
-	uint32_t *stage_rgba = nullptr, *stage_iters = nullptr;
+	uint32_t *stage_rgba = nullptr, *stage_iters = nullptr, *stage_fetches = nullptr;
 	hd_hit_record *stage_hits = nullptr;
 	uint64_t stage_pixels = 0;
 	hd_trace_params *params_dev = nullptr;

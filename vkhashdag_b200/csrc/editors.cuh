@@ -123,12 +123,19 @@ __device__ inline EditType edit_node(const hd_edit_desc &d, uint32_t bits, uint3
 		return min_n2 > d.r2 ? kNotAffected : kProceed;
 	}
 	case HD_EDIT_TERRAIN_FILL: {
+		bool whole = true; // footprint fully inside the terrain patch (p1[1] = extent bits, 0 = whole world)
+		if (d.p1[1] != 0u) {
+			const uint64_t e = 1ull << d.p1[1], s = 1ull << bits;
+			if (lb[0] >= e || lb[2] >= e)
+				return kNotAffected;
+			whole = lb[0] + s <= e && lb[2] + s <= e;
+		}
 		uint32_t hmin, hmax;
 		terrain_bounds(d, lb[0], lb[2], bits, hmin, hmax);
-		if (ub[1] <= hmin)
-			return kFill;
 		if (lb[1] >= hmax)
 			return kNotAffected;
+		if (whole && ub[1] <= hmin)
+			return kFill;
 		return kProceed;
 	}
 	}
@@ -147,6 +154,8 @@ __device__ inline bool voxel_in_range(const hd_edit_desc &d, uint32_t x, uint32_
 		return uint64_t(dx * dx + dy * dy + dz * dz) <= d.r2;
 	}
 	case HD_EDIT_TERRAIN_FILL:
+		if (d.p1[1] != 0u && ((x >> d.p1[1]) != 0u || (z >> d.p1[1]) != 0u))
+			return false;
 		return y < terrain_height(d, x, z);
 	}
 	return false;

@@ -163,6 +163,7 @@ void hd_pool_destroy(hd_pool *p) {
 	cudaFree(p->color_leaves);
 	cudaFree(p->stage_rgba);
 	cudaFree(p->stage_iters);
+	cudaFree(p->stage_fetches);
 	cudaFree(p->stage_hits);
 	cudaFree(p->params_dev);
 	cudaFree(p->dirty_scratch);
