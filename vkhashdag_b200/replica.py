@@ -1,0 +1,66 @@
+"""vkhashdag_b200/replica.py — multi-GPU plumbing: one process per GPU, pool replicated, frame sharded by screen tile.
+
+Trace needs no collective (every rank owns the tiles t % world == rank of hd_tile_shard).  Edits run on ONE rank; its
+dirty ranges reach the replicas through ONE broadcast of the packed staging buffer (hd_dirty_pack_dev /
+hd_dirty_apply_dev), which replaces DAGNodePool::Flush (src/DAGNodePool.cpp:56-85) for the replicated case.  The
+root is published last on every replica (ordering contract of src/main.cpp:281-296).
+
+`dist` is torch.distributed (backend "nccl" on GPUs; "gloo" in the CPU tests, which drive the same protocol with a
+host-memory stand-in for the pool).
+"""
+import torch
+
+
+def tile_owner(tile_index, world):
+    """Rank that owns screen tile t (hd_tile_shard: round-robin in row-major tile order)."""
+    return tile_index % world
+
+
+def local_tiles(width, height, tile_w, tile_h, rank, world):
+    """[(local_index, tile_x, tile_y)] of the tiles a rank owns, in its output order."""
+    tiles_x, tiles_y = -(-width // tile_w), -(-height // tile_h)
+    return [(lt, t % tiles_x, t // tiles_x) for lt, t in enumerate(range(rank, tiles_x * tiles_y, world))]
+
+
+def assemble_frame(parts, width, height, tile_w, tile_h, world, dtype=None):
+    """Stitch per-rank tile-major planes (index = rank) back into a row-major frame (host-side, for checks/display)."""
+    import numpy as np
+    frame = np.zeros((height, width), dtype=dtype or parts[0].dtype)
+    for rank, part in enumerate(parts):
+        for lt, tx, ty in local_tiles(width, height, tile_w, tile_h, rank, world):
+            x0, y0 = tx * tile_w, ty * tile_h
+            w, h = min(tile_w, width - x0), min(tile_h, height - y0)
+            blk = part[lt * tile_w * tile_h:(lt + 1) * tile_w * tile_h].reshape(tile_h, tile_w)
+            frame[y0:y0 + h, x0:x0 + w] = blk[:h, :w]
+    return frame
+
+
+class ReplicaSync:
+    """Broadcast the editing rank's dirty ranges to every replica with one payload collective per edit batch."""
+
+    def __init__(self, pool, dist, device, capacity_bytes=64 << 20):
+        self.pool, self.dist, self.device = pool, dist, device
+        self.staging = torch.empty(capacity_bytes, dtype=torch.uint8, device=device)
+        self.size = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def _grow(self, need):
+        if need > self.staging.numel():
+            self.staging = torch.empty(int(need * 1.5), dtype=torch.uint8, device=self.device)
+
+    def publish(self, src=0):
+        """Call on EVERY rank after rank `src` edited (and set its root).  Returns the packed size in bytes."""
+        rank = self.dist.get_rank()
+        if rank == src:
+            _, need = self.pool.DirtyCount()
+            self._grow(need)
+            n = self.pool.DirtyPack(self.staging.data_ptr(), self.staging.numel())
+            self.size[0] = n
+        self.dist.broadcast(self.size, src)            # 8 bytes: lets replicas size the payload collective
+        n = int(self.size[0])
+        self._grow(n)
+        self.dist.broadcast(self.staging[:n], src)     # ONE payload broadcast (NCCL over NVLink on GPUs)
+        if rank == src:
+            self.pool.DirtyReset()
+        else:
+            self.pool.DirtyApply(self.staging.data_ptr(), n)   # scatter kernel, bucket_words, root last
+        return n
