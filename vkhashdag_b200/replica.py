@@ -48,7 +48,17 @@ class ReplicaSync:
             self.staging = torch.empty(int(need * 1.5), dtype=torch.uint8, device=self.device)
 
     def publish(self, src=0):
-        """Call on EVERY rank after rank `src` edited (and set its root).  Returns the packed size in bytes."""
+        """Call on EVERY rank after rank `src` edited (and set its root).  Returns the packed size in bytes.
+
+        On GPUs the collectives are issued with the pool's stream current, so NCCL orders itself after the pack
+        kernels and the scatter kernel after the broadcast without host synchronisation in between."""
+        if torch.device(self.device).type == "cuda":
+            stream = torch.cuda.ExternalStream(self.pool.stream, device=torch.device(self.device))
+            with torch.cuda.stream(stream):
+                return self._publish(src)
+        return self._publish(src)
+
+    def _publish(self, src):
         rank = self.dist.get_rank()
         if rank == src:
             _, need = self.pool.DirtyCount()
