@@ -75,6 +75,16 @@ def default_config(level_count=17, top_level_count=9, word_bits_per_page=9, page
     return cfg
 
 
+def custom_config(bucket_bits_each_level, word_bits_per_page=9, page_bits_per_bucket=2):
+    """Config with an explicit per-level bucket count (Config::bucket_bits_each_level, Config.hpp:21)."""
+    cfg = HdConfig()
+    cfg.word_bits_per_page, cfg.page_bits_per_bucket = word_bits_per_page, page_bits_per_bucket
+    cfg.node_levels = len(bucket_bits_each_level)
+    for l, b in enumerate(bucket_bits_each_level):
+        cfg.bucket_bits_each_level[l] = b
+    return cfg
+
+
 def aabb(lo, hi):
     d = HdEditDesc()
     d.kind = EDIT_AABB_FILL
