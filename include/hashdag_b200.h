@@ -199,7 +199,7 @@ hd_status hd_traverse_ray(hd_pool *pool, uint32_t root, const float o[3], const 
 /* ---- replica sync: replaces DAGNodePool::Flush for the multi-GPU case ----
  * Buckets are append-only, so the dirty set is [words at last sync, bucket_words) of every bucket.  The editing
  * rank packs it into one staging buffer (u32 words)
- *   [n_ranges][payload_words][root][0]  n_ranges x {word_offset, word_count, payload_offset}  payload...
+ *   [n_ranges][payload_words][root][clear_first]  n_ranges x {word_offset, word_count, payload_offset}  payload...
  * which the caller broadcasts (one NCCL broadcast over NVLink); replicas apply it with a scatter kernel that also
  * advances their bucket_words, and publish the root last. */
 hd_status hd_dirty_count(hd_pool *pool, uint32_t *n_ranges, uint64_t *packed_bytes);
@@ -207,6 +207,17 @@ hd_status hd_dirty_ranges(hd_pool *pool, hd_dirty_range *out, uint32_t capacity,
 hd_status hd_dirty_pack_dev(hd_pool *pool, void *staging_dev, uint64_t capacity_bytes, uint64_t *packed_bytes);
 hd_status hd_dirty_apply_dev(hd_pool *pool, const void *staging_dev, uint64_t packed_bytes);
 hd_status hd_dirty_reset(hd_pool *pool);
+
+/* ---- garbage collection: replaces NodePoolThreadedGC::ThreadedGC (NodePoolThreadedGC.hpp:372-403; row N1) ----
+ * Keeps exactly the nodes reachable from roots[0..n) plus the filled nodes, re-hashes them into compacted buckets and
+ * returns the remapped roots (pointers change, the DAG does not).  The pool's published root follows when it is one
+ * of `roots`.  Replicas must be re-synchronised afterwards (the next hd_dirty_pack_dev carries a clear-first flag). */
+hd_status hd_gc(hd_pool *pool, const uint32_t *roots, uint32_t n_roots, uint32_t *new_roots, uint64_t *reachable_nodes);
+
+/* ---- serialisation (no reference counterpart: it rebuilds its scene procedurally at start; row N4) ----
+ * One file holds the config, the used prefix of every bucket, bucket_words, the root and the colour buffers. */
+hd_status hd_pool_save(hd_pool *pool, const char *path);
+hd_status hd_pool_load(const char *path, int device, hd_pool **out);
 
 /* ---- introspection used by tests / benches ---- */
 hd_status hd_pool_used_words(hd_pool *pool, uint64_t *out); /* sum of bucket_words */

@@ -6,7 +6,7 @@
 //   NodePointer / NodeCoord           include/hashdag/NodePointer.hpp:13-31, NodeCoord.hpp:14-94
 //   EditType / IterateType            include/hashdag/Editor.hpp:18, test/test.cpp:36-52
 //   AABBEditor / SphereEditor<Mode>   src/main.cpp:32-150 (as POD descriptors: device predicates are compiled in)
-//   DAGNodePool::{Create, GetConfig, Edit, ThreadedEdit, Traversal<float>, Iterate, SetRoot, GetRoot, Flush}
+//   DAGNodePool::{Create, GetConfig, Edit, ThreadedEdit, ThreadedGC, Traversal<float>, Iterate, SetRoot, GetRoot, Flush}
 //                                     src/DAGNodePool.hpp:84-99, NodePool.hpp:404-417, NodePoolThreadedEdit.hpp:104-126,
 //                                     NodePoolTraversal.hpp:93-256
 // All compute happens in libhashdag_b200.so on the GPU; this header only marshals.
@@ -229,6 +229,40 @@ public:
 	template <typename Iterator_T> void Iterate(NodePointer<uint32_t> root, Iterator_T *p_iterator) const {
 		std::unordered_map<uint32_t, std::array<uint32_t, 9>> cache;
 		iterate_node(root, NodeCoord<uint32_t>{}, p_iterator, cache);
+	}
+
+	// NodePoolThreadedGC::ThreadedGC (NodePoolThreadedGC.hpp:394-403): compacts the pool on the GPU, returns the
+	// relocated root(s).  The thread pool argument is accepted for source compatibility and ignored.
+	NodePointer<uint32_t> ThreadedGC(void * /*lf::busy_pool* */, NodePointer<uint32_t> root) {
+		uint32_t in = *root, out = *root;
+		m_last_status = hd_gc(m_pool, &in, 1, &out, nullptr);
+		return m_last_status == HD_OK ? NodePointer<uint32_t>{out} : root;
+	}
+	std::vector<NodePointer<uint32_t>> ThreadedGC(void *, std::vector<NodePointer<uint32_t>> roots) {
+		std::vector<uint32_t> in(roots.size()), out(roots.size());
+		for (size_t i = 0; i < roots.size(); ++i)
+			in[i] = *roots[i];
+		m_last_status = hd_gc(m_pool, in.data(), uint32_t(in.size()), out.data(), nullptr);
+		if (m_last_status == HD_OK)
+			for (size_t i = 0; i < roots.size(); ++i)
+				roots[i] = NodePointer<uint32_t>{out[i]};
+		return roots;
+	}
+
+	// pool file (no reference counterpart)
+	bool Save(const char *path) { return (m_last_status = hd_pool_save(m_pool, path)) == HD_OK; }
+	static std::unique_ptr<DAGNodePool> Load(const char *path, int device = 0) {
+		hd_pool *h = nullptr;
+		if (hd_pool_load(path, device, &h) != HD_OK)
+			return nullptr;
+		hd_config c{};
+		hd_pool_get_config(h, &c);
+		Config<uint32_t> cfg;
+		cfg.word_bits_per_page = c.word_bits_per_page, cfg.page_bits_per_bucket = c.page_bits_per_bucket;
+		cfg.bucket_bits_each_level.assign(c.bucket_bits_each_level, c.bucket_bits_each_level + c.node_levels);
+		std::unique_ptr<DAGNodePool> p{new DAGNodePool(std::move(cfg))};
+		p->m_pool = h;
+		return p;
 	}
 
 	// Frame trace: TracePass::CmdExecute + trace.frag main() (TracePass.cpp:106-139); host output planes

@@ -77,6 +77,7 @@ class Oracle(_Lib):
         L.orc_terrain_height.restype = u32
         L.orc_terrain_height.argtypes = [C.POINTER(HdEditDesc), u32, u32]
         L.orc_canonical.argtypes = [pu32, u32, u32, C.POINTER(u64)]
+        L.orc_count_stored_nodes.argtypes = [pu32, pu32, C.POINTER(HdConfig), C.POINTER(u64)]
         L.orc_voxel_get.restype = C.c_int
         L.orc_voxel_get.argtypes = [pu32, u32, u32, u32, u32, u32]
         L.orc_traverse.restype = C.c_int
@@ -105,6 +106,12 @@ class Oracle(_Lib):
         self.lib.orc_canonical(words_ptr, node_levels, root, out)
         return {"hash": out[0], "by_ptr": out[1], "by_content": out[2], "voxels": out[3],
                 "per_level": [out[4 + i] for i in range(node_levels)]}
+
+    def count_stored_nodes(self, pool):
+        """[stored node count per level] by walking every bucket of a host pool/mirror."""
+        out = (C.c_uint64 * pool.cfg.node_levels)()
+        self.lib.orc_count_stored_nodes(pool.words_ptr, pool.bucket_words_ptr, C.byref(pool.cfg), out)
+        return list(out)
 
     def voxel_get(self, words_ptr, node_levels, root, x, y, z):
         return bool(self.lib.orc_voxel_get(words_ptr, node_levels, root, x, y, z))
@@ -263,6 +270,8 @@ class Ref(_Lib):
         L.ref_edit.argtypes = [vp, u32, C.POINTER(HdEditDesc), u32, u32]
         L.ref_edit_batch.restype = u32
         L.ref_edit_batch.argtypes = [vp, u32, C.POINTER(HdEditDesc), u32, u32, u32]
+        L.ref_gc.restype = u32
+        L.ref_gc.argtypes = [vp, u32, u32]
         L.ref_traverse.restype = C.c_int
         L.ref_traverse.argtypes = [vp, u32, pf, pf, pf]
         L.ref_trace_frame_host.restype = u64
@@ -346,6 +355,10 @@ class RefPool(_PoolBase):
     def edit_batch(self, root, edits, threads=0, max_task_level=10):
         arr = edit_array(edits)
         return self.L.ref_edit_batch(self.h, root, arr, len(edits), threads, max_task_level)
+
+    def gc(self, root, threads=4):
+        """NodePoolThreadedGC::ThreadedGC: compacts the pool, returns the relocated root."""
+        return self.L.ref_gc(self.h, root, threads)
 
     def traverse(self, root, o, d):
         o3, d3, out = (C.c_float * 3)(*o), (C.c_float * 3)(*d), (C.c_float * 3)()

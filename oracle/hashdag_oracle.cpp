@@ -944,6 +944,33 @@ void orc_canonical(const uint32_t *words, uint32_t node_levels, uint32_t root, u
 	out[3] = c.count(root, 0);
 }
 
+// Nodes physically stored in a pool (walk of every bucket, node sizes as find_node_in_span steps them,
+// NodePool.hpp:79-91): out[level] = stored node count.  Used to prove a GC left no unreachable node behind.
+void orc_count_stored_nodes(const uint32_t *words, const uint32_t *bucket_words, const hd_config *cfg, uint64_t *out) {
+	Geometry g;
+	if (!make_geometry(*cfg, g))
+		return;
+	const uint32_t wpp = g.words_per_page();
+	for (uint32_t l = 0; l < g.node_levels(); ++l) {
+		out[l] = 0;
+		const bool is_leaf = l == g.node_levels() - 1;
+		for (uint32_t b = 0; b < (1u << cfg->bucket_bits_each_level[l]); ++b) {
+			const uint32_t bucket = g.level_base[l] + b, bw = bucket_words[bucket];
+			const uint32_t *base = words + (size_t(bucket) << g.bucket_shift());
+			for (uint32_t page = 0; page < bw; page += wpp) {
+				const uint32_t end = std::min(page + wpp, bw);
+				for (uint32_t it = page; it < end;) {
+					const uint32_t sz = is_leaf ? 2u : (uint8_t(base[it]) ? 1u + uint32_t(__builtin_popcount(uint8_t(base[it]))) : 0u);
+					if (sz == 0)
+						break;
+					++out[l];
+					it += sz;
+				}
+			}
+		}
+	}
+}
+
 // Voxel lookup (the reconstructed Iterate intent, test/test.cpp:36-52,173-198): is voxel (x,y,z) set?
 int orc_voxel_get(const uint32_t *words, uint32_t node_levels, uint32_t root, uint32_t x, uint32_t y, uint32_t z) {
 	if (root == kNull)

@@ -18,10 +18,12 @@
 
 #include <hashdag/NodePool.hpp>
 #include <hashdag/NodePoolThreadedEdit.hpp>
+#include <hashdag/NodePoolThreadedGC.hpp>
 #include <hashdag/NodePoolTraversal.hpp>
 #include <hashdag/VBREditor.hpp>
 
 #include <libfork/schedule/busy_pool.hpp>
+#include <parallel_hashmap/phmap.h>
 
 #include <array>
 #include <atomic>
@@ -38,10 +40,16 @@ using Cfg = hashdag::Config<uint32_t>;
 using Coord = hashdag::NodeCoord<uint32_t>;
 using NPtr = hashdag::NodePointer<uint32_t>;
 
+namespace ref_phmap { // as src/DAGNodePool.hpp:26-29
+template <typename K, typename V> using flat_hash_map = phmap::flat_hash_map<K, V>;
+template <typename K> using flat_hash_set = phmap::flat_hash_set<K>;
+} // namespace ref_phmap
+
 // ------------------------------------------------------------------------------------------------ pool
 struct RefPool final : public hashdag::NodePoolBase<RefPool, uint32_t>,
                        public hashdag::NodePoolTraversal<RefPool, uint32_t>,
-                       public hashdag::NodePoolThreadedEdit<RefPool, uint32_t> {
+                       public hashdag::NodePoolThreadedEdit<RefPool, uint32_t>,
+                       public hashdag::NodePoolThreadedGC<RefPool, uint32_t, ref_phmap::flat_hash_map, ref_phmap::flat_hash_set> {
 	using WordSpanHasher = hashdag::MurmurHasher32;
 	uint32_t *memory = nullptr;
 	uint64_t total_words = 0;
@@ -69,6 +77,7 @@ struct RefPool final : public hashdag::NodePoolBase<RefPool, uint32_t>,
 	void WritePage(uint32_t page, uint32_t off, std::span<const uint32_t> w) {
 		std::copy(w.begin(), w.end(), memory + (uint64_t(page) << GetConfig().word_bits_per_page) + off);
 	}
+	void FreePage(uint32_t) {} // GCNodePool concept (NodePool.hpp:37-38); the flat mapping keeps its pages
 };
 
 // --------------------------------------------------------------------------------------------- editors
@@ -437,6 +446,11 @@ uint32_t ref_edit_batch(ref_pool *p, uint32_t root, const hd_edit_desc *d, uint3
 	for (uint32_t i = 0; i < n; ++i)
 		root = ref_edit(p, root, d + i, threads, max_task_level);
 	return root;
+}
+
+// NodePoolThreadedGC::ThreadedGC (NodePoolThreadedGC.hpp:394-397): returns the relocated root
+uint32_t ref_gc(ref_pool *p, uint32_t root, uint32_t threads) {
+	return *p->pool->ThreadedGC(get_busy_pool(threads ? threads : 1), NPtr{root});
 }
 
 int ref_traverse(ref_pool *p, uint32_t root, const float o[3], const float d[3], float out[3]) {

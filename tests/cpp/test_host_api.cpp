@@ -114,6 +114,17 @@ int main() {
 		                               SphereEditor<EditMode::kDig>{{310, 300, 300}, 900}),
 		                    AABBEditor{{280, 280, 280}, {290, 290, 290}});
 		CHECK(a && a == b); // same pool: identical content dedups to the identical pointer
+		// GC (main.cpp:235-238,373-378): the dug version survives, its pick ray is unchanged; save / load round trip
+		auto kept = pool->ThreadedGC(nullptr, dug);
+		CHECK(kept && pool->GetLastStatus() == HD_OK);
+		auto hit3 = pool->Traversal<float>(kept, {0.5f, 0.5f, 1.5f}, {0.f, 0.f, -1.f});
+		CHECK(hit3 && hit3->z == hit2->z);
+		pool->SetRoot(kept);
+		CHECK(pool->Save("/tmp/hashdag_b200_cpp_test.hdag"));
+		auto loaded = DAGNodePool::Load("/tmp/hashdag_b200_cpp_test.hdag");
+		CHECK(loaded && loaded->GetRoot() == kept && loaded->GetConfig().GetNodeLevels() == 9);
+		auto hit4 = loaded->Traversal<float>(loaded->GetRoot(), {0.5f, 0.5f, 1.5f}, {0.f, 0.f, -1.f});
+		CHECK(hit4 && hit4->z == hit2->z);
 	}
 	std::puts("cpp host api: OK");
 	return 0;

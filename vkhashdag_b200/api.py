@@ -60,7 +60,8 @@ SYMBOLS = [
     "hd_pool_upload_bucket_words", "hd_pool_read_bucket_words", "hd_pool_filled_nodes", "hd_edit_batch",
     "hd_upsert_nodes", "hd_color_upload", "hd_trace", "hd_trace_dev", "hd_trace_tiles", "hd_trace_tiles_dev",
     "hd_tile_shard_pixels", "hd_traverse_ray", "hd_dirty_count", "hd_dirty_ranges", "hd_dirty_pack_dev",
-    "hd_dirty_apply_dev", "hd_dirty_reset", "hd_pool_used_words", "hd_sync", "hd_kernel_launches",
+    "hd_dirty_apply_dev", "hd_dirty_reset", "hd_pool_used_words", "hd_sync", "hd_kernel_launches", "hd_pool_save",
+    "hd_pool_load", "hd_gc",
 ]
 
 
@@ -117,6 +118,9 @@ def lib():
     L.hd_dirty_pack_dev.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.hd_dirty_apply_dev.argtypes = [vp, vp, u64]
     L.hd_dirty_reset.argtypes = [vp]
+    L.hd_gc.argtypes = [vp, pu32, u32, pu32, C.POINTER(u64)]
+    L.hd_pool_save.argtypes = [vp, C.c_char_p]
+    L.hd_pool_load.argtypes = [C.c_char_p, ci, C.POINTER(vp)]
     L.hd_pool_used_words.argtypes = [vp, C.POINTER(u64)]
     L.hd_sync.argtypes = [vp]
     L.hd_kernel_launches.restype = u64
@@ -171,6 +175,31 @@ class DAGNodePool:
     @classmethod
     def Create(cls, config, device=0):
         return cls(config, device)
+
+    @classmethod
+    def Load(cls, path, device=0):
+        """hd_pool_load: a pool file written by Save (config, nodes, root, colour buffers)."""
+        self = cls.__new__(cls)
+        self._h, self._L, self.device, self.last_stats = C.c_void_p(), lib(), device, None
+        _check(self._L.hd_pool_load(os.fsencode(path), device, C.byref(self._h)))
+        self.config = HdConfig()
+        _check(self._L.hd_pool_get_config(self._h, C.byref(self.config)))
+        return self
+
+    def ThreadedGC(self, roots):
+        """NodePoolThreadedGC::ThreadedGC (NodePoolThreadedGC.hpp:394-403): accepts one root or a list; returns the
+        remapped root(s).  self.last_gc_nodes = reachable unique nodes kept (filled nodes included)."""
+        single = isinstance(roots, int)
+        arr = np.ascontiguousarray([roots] if single else roots, dtype=np.uint32)
+        out = np.empty_like(arr)
+        kept = C.c_uint64()
+        _check(self._L.hd_gc(self._h, arr.ctypes.data_as(C.POINTER(C.c_uint32)), arr.size,
+                             out.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(kept)))
+        self.last_gc_nodes = kept.value
+        return int(out[0]) if single else [int(v) for v in out]
+
+    def Save(self, path):
+        _check(self._L.hd_pool_save(self._h, os.fsencode(path)))
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:

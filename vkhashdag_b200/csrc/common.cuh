@@ -76,6 +76,7 @@ struct hd_pool {
 	uint64_t color_node_words = 0, color_leaf_words = 0;
 
 	uint32_t root = HD_NULL_NODE;
+	bool needs_full_resync = false; // set by hd_gc: replicas must clear before applying the next sync
 	std::vector<uint32_t> filled; // m_filled_node_pointers (NodePool.hpp:54)
 
 	// trace staging (device) for the host-pointer entry points
@@ -94,4 +95,7 @@ struct hd_pool {
 namespace hd {
 hd_status edit_scratch_free(hd_pool *pool);
 hd_status ensure_filled(hd_pool *pool);
+hd_status upsert_batch_dev(hd_pool *pool, uint32_t level, uint32_t n, uint32_t stride, const uint32_t *cand_dev,
+                           uint32_t *result_dev);
+hd_status set_filled(hd_pool *pool, const std::vector<uint32_t> &filled);
 } // namespace hd

@@ -760,6 +760,42 @@ static hd_status run_upsert(hd_pool *p, uint32_t level, uint32_t n, uint32_t str
 	return HD_OK;
 }
 
+// Find-or-insert of n packed nodes already on the device (all are candidates); result[i] = pointer.  Used by the GC.
+hd_status upsert_batch_dev(hd_pool *p, uint32_t level, uint32_t n, uint32_t stride, const uint32_t *cand_dev,
+                           uint32_t *result_dev) {
+	if (n == 0)
+		return HD_OK;
+	hd_status st = scratch_init(p);
+	if (st != HD_OK)
+		return st;
+	cudaStream_t s = p->stream;
+	uint32_t *winner = nullptr;
+	uint8_t *state = nullptr;
+	HD_CUDA_TRY(amalloc(&winner, n, s));
+	HD_CUDA_TRY(amalloc(&state, n, s));
+	HD_CUDA_TRY(cudaMemsetAsync(result_dev, 0xFF, uint64_t(n) * 4, s));
+	k_fill_u8<<<grid_for(n), kBlock, 0, s>>>(state, n, 1);
+	HD_LAUNCH_CHECK();
+	st = run_upsert(p, level, n, stride, cand_dev, state, winner, nullptr, result_dev);
+	if (st == HD_OK) {
+		k_resolve_flat<<<grid_for(n), kBlock, 0, s>>>(n, state, winner, result_dev);
+		HD_LAUNCH_CHECK();
+	}
+	cudaFreeAsync(winner, s), cudaFreeAsync(state, s);
+	return st;
+}
+
+// install new filled-node pointers (after a GC moved them)
+hd_status set_filled(hd_pool *p, const std::vector<uint32_t> &filled) {
+	hd_status st = scratch_init(p);
+	if (st != HD_OK)
+		return st;
+	p->filled = filled;
+	HD_CUDA_TRY(cudaMemcpyAsync(p->edit->filled_dev, p->filled.data(), p->filled.size() * 4, cudaMemcpyHostToDevice, p->stream));
+	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	return HD_OK;
+}
+
 hd_status ensure_filled(hd_pool *p) { // make_filled_node_pointers, NodePool.hpp:240-262
 	if (!p->filled.empty())
 		return HD_OK;

@@ -10,6 +10,9 @@
 // payload_offset} then the payload.
 #include "common.cuh"
 
+#include <algorithm>
+#include <cstring>
+
 namespace hd {
 
 constexpr uint32_t kHeaderWords = 4;
@@ -158,8 +161,8 @@ hd_status hd_dirty_pack_dev(hd_pool *p, void *staging_dev, uint64_t capacity_byt
 		k_dirty_gather<<<std::min<uint32_t>(h[0], 148u * 8u), 256, 0, p->stream>>>(p->words, stg, ranges, payload);
 		HD_LAUNCH_CHECK();
 	}
-	const uint32_t root = p->root;
-	HD_CUDA_TRY(cudaMemcpyAsync(stg + 2, &root, 4, cudaMemcpyHostToDevice, p->stream));
+	const uint32_t tail[2] = {p->root, p->needs_full_resync ? 1u : 0u}; // [3] = 1: replicas clear before applying (after a GC)
+	HD_CUDA_TRY(cudaMemcpyAsync(stg + 2, tail, 8, cudaMemcpyHostToDevice, p->stream));
 	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
 	return HD_OK;
 }
@@ -176,6 +179,11 @@ hd_status hd_dirty_apply_dev(hd_pool *p, const void *staging_dev, uint64_t packe
 		set_error("staging buffer truncated");
 		return HD_ERR_INVALID;
 	}
+	if (h[3] == 1u) { // the sender compacted its pool: every pointer changed, start from an empty replica
+		hd_status cs = hd_pool_clear(p);
+		if (cs != HD_OK)
+			return cs;
+	}
 	if (h[0]) {
 		const uint32_t *ranges = stg + kHeaderWords, *payload = ranges + size_t(h[0]) * 3;
 		k_dirty_scatter<<<std::min<uint32_t>(h[0], 148u * 8u), 256, 0, p->stream>>>(
@@ -187,6 +195,125 @@ hd_status hd_dirty_apply_dev(hd_pool *p, const void *staging_dev, uint64_t packe
 	return HD_OK;
 }
 
+// ---- pool serialisation (the reference has no on-disk format) ---------------------------------------
+// File = FileHeader, then the same packed staging blob replica sync uses (every non-empty bucket's used prefix as one
+// range, root in the blob header), then the two colour buffers.
+struct FileHeader {
+	char magic[8]; // "HDAGB200"
+	uint32_t version;
+	hd_config cfg;
+	uint64_t blob_bytes, color_node_words, color_leaf_words;
+};
+
+hd_status hd_pool_save(hd_pool *p, const char *path) {
+	if (!p || !path)
+		return HD_ERR_INVALID;
+	HD_CUDA_TRY(cudaSetDevice(p->device));
+	const uint32_t nb = p->geo.total_buckets;
+	uint32_t *zeros = nullptr, *stg = nullptr;
+	HD_CUDA_TRY(cudaMalloc(&zeros, size_t(nb) * 4));
+	HD_CUDA_TRY(cudaMemsetAsync(zeros, 0, size_t(nb) * 4, p->stream));
+	hd_status s = ensure_dirty_scratch(p, kHeaderWords * 4);
+	if (s != HD_OK)
+		return s;
+	HD_CUDA_TRY(cudaMemsetAsync(p->dirty_scratch, 0, kHeaderWords * 4, p->stream));
+	k_dirty_scan<<<(nb + 255) / 256, 256, 0, p->stream>>>(p->bucket_words, zeros, nb, p->geo.bucket_shift(),
+	                                                      p->dirty_scratch, nullptr, 0);
+	HD_LAUNCH_CHECK();
+	uint32_t h[kHeaderWords];
+	HD_CUDA_TRY(cudaMemcpyAsync(h, p->dirty_scratch, sizeof(h), cudaMemcpyDeviceToHost, p->stream));
+	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	const uint64_t blob = (uint64_t(kHeaderWords) + uint64_t(h[0]) * 3 + h[1]) * 4;
+	HD_CUDA_TRY(cudaMalloc(&stg, blob));
+	HD_CUDA_TRY(cudaMemsetAsync(stg, 0, kHeaderWords * 4, p->stream));
+	k_dirty_scan<<<(nb + 255) / 256, 256, 0, p->stream>>>(p->bucket_words, zeros, nb, p->geo.bucket_shift(), stg,
+	                                                      stg + kHeaderWords, h[0]);
+	HD_LAUNCH_CHECK();
+	if (h[0]) {
+		k_dirty_gather<<<std::min<uint32_t>(h[0], 148u * 8u), 256, 0, p->stream>>>(p->words, stg, stg + kHeaderWords,
+		                                                                          stg + kHeaderWords + size_t(h[0]) * 3);
+		HD_LAUNCH_CHECK();
+	}
+	std::vector<uint32_t> host(blob / 4);
+	HD_CUDA_TRY(cudaMemcpyAsync(host.data(), stg, blob, cudaMemcpyDeviceToHost, p->stream));
+	std::vector<uint32_t> cn(p->color_node_words), cl(p->color_leaf_words);
+	if (!cn.empty())
+		HD_CUDA_TRY(cudaMemcpyAsync(cn.data(), p->color_nodes, cn.size() * 4, cudaMemcpyDeviceToHost, p->stream));
+	if (!cl.empty())
+		HD_CUDA_TRY(cudaMemcpyAsync(cl.data(), p->color_leaves, cl.size() * 4, cudaMemcpyDeviceToHost, p->stream));
+	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	cudaFree(zeros), cudaFree(stg);
+	host[2] = p->root;
+	FileHeader fh{};
+	memcpy(fh.magic, "HDAGB200", 8);
+	fh.version = 1, fh.cfg = p->cfg, fh.blob_bytes = blob;
+	fh.color_node_words = cn.size(), fh.color_leaf_words = cl.size();
+	FILE *f = fopen(path, "wb");
+	if (!f) {
+		set_error("cannot open %s for writing", path);
+		return HD_ERR_INVALID;
+	}
+	bool ok = fwrite(&fh, sizeof(fh), 1, f) == 1 && fwrite(host.data(), 1, blob, f) == blob;
+	ok = ok && (cn.empty() || fwrite(cn.data(), 4, cn.size(), f) == cn.size());
+	ok = ok && (cl.empty() || fwrite(cl.data(), 4, cl.size(), f) == cl.size());
+	ok = (fclose(f) == 0) && ok;
+	if (!ok) {
+		set_error("short write to %s", path);
+		return HD_ERR_INVALID;
+	}
+	return HD_OK;
+}
+
+hd_status hd_pool_load(const char *path, int device, hd_pool **out) {
+	if (!path || !out)
+		return HD_ERR_INVALID;
+	*out = nullptr;
+	FILE *f = fopen(path, "rb");
+	if (!f) {
+		set_error("cannot open %s", path);
+		return HD_ERR_INVALID;
+	}
+	FileHeader fh{};
+	std::vector<uint32_t> blob, cn, cl;
+	bool ok = fread(&fh, sizeof(fh), 1, f) == 1 && memcmp(fh.magic, "HDAGB200", 8) == 0 && fh.version == 1 &&
+	          fh.blob_bytes >= kHeaderWords * 4 && fh.blob_bytes % 4 == 0;
+	if (ok) {
+		blob.resize(fh.blob_bytes / 4), cn.resize(fh.color_node_words), cl.resize(fh.color_leaf_words);
+		ok = fread(blob.data(), 1, fh.blob_bytes, f) == fh.blob_bytes;
+		ok = ok && (cn.empty() || fread(cn.data(), 4, cn.size(), f) == cn.size());
+		ok = ok && (cl.empty() || fread(cl.data(), 4, cl.size(), f) == cl.size());
+	}
+	fclose(f);
+	if (!ok) {
+		set_error("%s is not a valid hashdag_b200 pool file", path);
+		return HD_ERR_INVALID;
+	}
+	hd_pool *p = nullptr;
+	hd_status s = hd_pool_create(&fh.cfg, device, &p);
+	if (s != HD_OK)
+		return s;
+	uint32_t *stg = nullptr;
+	cudaError_t e = cudaMalloc(&stg, fh.blob_bytes);
+	if (e == cudaSuccess)
+		e = cudaMemcpy(stg, blob.data(), fh.blob_bytes, cudaMemcpyHostToDevice);
+	if (e != cudaSuccess) {
+		set_error("pool load: %s", cudaGetErrorString(e));
+		cudaFree(stg);
+		hd_pool_destroy(p);
+		return HD_ERR_CUDA;
+	}
+	s = hd_dirty_apply_dev(p, stg, fh.blob_bytes);
+	cudaFree(stg);
+	if (s == HD_OK && (!cn.empty() || !cl.empty()))
+		s = hd_color_upload(p, cn.data(), cn.size(), cl.data(), cl.size());
+	if (s != HD_OK) {
+		hd_pool_destroy(p);
+		return s;
+	}
+	*out = p;
+	return HD_OK;
+}
+
 hd_status hd_dirty_reset(hd_pool *p) {
 	if (!p)
 		return HD_ERR_INVALID;
@@ -194,6 +321,7 @@ hd_status hd_dirty_reset(hd_pool *p) {
 	HD_CUDA_TRY(cudaMemcpyAsync(p->bucket_synced, p->bucket_words, size_t(p->geo.total_buckets) * 4,
 	                            cudaMemcpyDeviceToDevice, p->stream));
 	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	p->needs_full_resync = false;
 	return HD_OK;
 }
 
