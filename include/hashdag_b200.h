@@ -189,6 +189,13 @@ hd_status hd_trace_tiles(hd_pool *pool, const hd_trace_params *params, const hd_
                          const hd_trace_outputs *host_out);
 hd_status hd_trace_tiles_dev(hd_pool *pool, const hd_trace_params *params, const hd_tile_shard *shard,
                              const hd_trace_outputs *dev_out);
+/* Pipelined frames: submit enqueues the trace of one frame and the asynchronous copy of its shaded rgba8 plane into
+ * host_rgba8 (pinned host memory for full overlap) on a copy stream; collect blocks until that frame has landed.
+ * Two slots (0/1) may be in flight, so the read-back of frame k overlaps the trace of frame k+1 (a frame loop with
+ * kFrameCount frames in flight, src/main.cpp:20,389-403).  shard may be NULL (full frame, row-major). */
+hd_status hd_trace_submit(hd_pool *pool, const hd_trace_params *params, const hd_tile_shard *shard, uint32_t *host_rgba8,
+                          uint32_t slot);
+hd_status hd_trace_collect(hd_pool *pool, uint32_t slot);
 /* pixels a rank owns under a shard (size of its output planes) */
 uint64_t hd_tile_shard_pixels(const hd_trace_params *params, const hd_tile_shard *shard);
 /* single pick ray: NodePoolTraversal::Traversal<float> (NodePoolTraversal.hpp:93-256), main.cpp:320-321.

@@ -111,3 +111,32 @@ def test_pick_ray_matches_host_traversal(oracle, hd):
             assert np.array_equal(exp.view(np.uint32), got.view(np.uint32))
     assert dev.Traversal(NULL, (0.5, 0.5, 1.5), (0, 0, -1)) is None
     dev.close()
+
+
+def test_pipelined_frames_equal_blocking_frames(oracle, hd):
+    """hd_trace_submit/collect (two frames in flight) returns the same frames as the blocking hd_trace."""
+    import torch
+    cfg, opool, root = build_scene(oracle, level_count=9)
+    dev = hd.DAGNodePool(cfg)
+    dev.UploadFrom(opool)
+    W, H = 640, 360
+    cams = [abi.camera_params(cfg, root, (0.5, 0.5 + 0.02 * i, 1.4), np.pi + 0.05 * i, -0.1, W, H) for i in range(7)]
+    want = [dev.Trace(P, want=("rgba8",))["rgba8"].copy() for P in cams]
+    for shard in (None, (64, 64, 1, 3)):
+        n = dev.ShardPixels(cams[0], shard) if shard else W * H
+        bufs = [torch.zeros(n, dtype=torch.int32).pin_memory() for _ in range(2)]
+        views = [b.numpy().view(np.uint32) for b in bufs]
+        got = []
+        for i, P in enumerate(cams):
+            slot = i & 1
+            if i >= 2:
+                dev.TraceCollect(slot)
+                got.append(views[slot].copy())
+            dev.TraceSubmit(P, views[slot], slot, shard=shard)
+        for i in range(len(cams) - 2, len(cams)):
+            dev.TraceCollect(i & 1)
+            got.append(views[i & 1].copy())
+        for i, P in enumerate(cams):
+            exp = want[i].reshape(-1) if shard is None else dev.Trace(P, want=("rgba8",), shard=shard)["rgba8"]
+            assert np.array_equal(got[i], exp), (i, shard)
+    dev.close()

@@ -61,7 +61,7 @@ SYMBOLS = [
     "hd_upsert_nodes", "hd_color_upload", "hd_trace", "hd_trace_dev", "hd_trace_tiles", "hd_trace_tiles_dev",
     "hd_tile_shard_pixels", "hd_traverse_ray", "hd_dirty_count", "hd_dirty_ranges", "hd_dirty_pack_dev",
     "hd_dirty_apply_dev", "hd_dirty_reset", "hd_pool_used_words", "hd_sync", "hd_kernel_launches", "hd_pool_save",
-    "hd_pool_load", "hd_gc",
+    "hd_pool_load", "hd_gc", "hd_trace_submit", "hd_trace_collect",
 ]
 
 
@@ -109,6 +109,8 @@ def lib():
     L.hd_trace_dev.argtypes = [vp, C.POINTER(HdTraceParams), C.POINTER(HdTraceOutputs)]
     L.hd_trace_tiles.argtypes = [vp, C.POINTER(HdTraceParams), C.POINTER(HdTileShard), C.POINTER(HdTraceOutputs)]
     L.hd_trace_tiles_dev.argtypes = [vp, C.POINTER(HdTraceParams), C.POINTER(HdTileShard), C.POINTER(HdTraceOutputs)]
+    L.hd_trace_submit.argtypes = [vp, C.POINTER(HdTraceParams), C.POINTER(HdTileShard), vp, u32]
+    L.hd_trace_collect.argtypes = [vp, u32]
     L.hd_tile_shard_pixels.restype = u64
     L.hd_tile_shard_pixels.argtypes = [C.POINTER(HdTraceParams), C.POINTER(HdTileShard)]
     L.hd_traverse_ray.argtypes = [vp, u32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(ci),
@@ -342,6 +344,18 @@ class DAGNodePool:
         else:
             shard = HdTileShard(*shard) if not isinstance(shard, HdTileShard) else shard
             _check(self._L.hd_trace_tiles_dev(self._h, C.byref(params), C.byref(shard), C.byref(o)))
+
+    def TraceSubmit(self, params, host_rgba8, slot, shard=None):
+        """hd_trace_submit: enqueue one frame + async read-back of its rgba8 plane into a host array (numpy, ideally
+        backed by pinned memory).  Pair with TraceCollect(slot); two slots may be in flight."""
+        sh = None
+        if shard is not None:
+            sh = HdTileShard(*shard) if not isinstance(shard, HdTileShard) else shard
+        _check(self._L.hd_trace_submit(self._h, C.byref(params), C.byref(sh) if sh is not None else None,
+                                       host_rgba8.ctypes.data, slot))
+
+    def TraceCollect(self, slot):
+        _check(self._L.hd_trace_collect(self._h, slot))
 
     def ShardPixels(self, params, shard):
         shard = HdTileShard(*shard) if not isinstance(shard, HdTileShard) else shard

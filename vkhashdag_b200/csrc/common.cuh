@@ -85,6 +85,13 @@ struct hd_pool {
 	uint64_t stage_pixels = 0;
 	hd_trace_params *params_dev = nullptr;
 
+	// pipelined frames (hd_trace_submit / hd_trace_collect): two slots, copy stream overlaps the next trace
+	cudaStream_t copy_stream = nullptr;
+	uint32_t *pipe_rgba[2] = {nullptr, nullptr};
+	uint64_t pipe_pixels[2] = {0, 0};
+	cudaEvent_t pipe_traced[2] = {nullptr, nullptr}, pipe_done[2] = {nullptr, nullptr};
+	bool pipe_busy[2] = {false, false};
+
 	hd::EditScratch *edit = nullptr;
 
 	// dirty-range scratch

@@ -167,6 +167,15 @@ void hd_pool_destroy(hd_pool *p) {
 	cudaFree(p->stage_hits);
 	cudaFree(p->params_dev);
 	cudaFree(p->dirty_scratch);
+	for (int i = 0; i < 2; ++i) {
+		cudaFree(p->pipe_rgba[i]);
+		if (p->pipe_traced[i])
+			cudaEventDestroy(p->pipe_traced[i]);
+		if (p->pipe_done[i])
+			cudaEventDestroy(p->pipe_done[i]);
+	}
+	if (p->copy_stream)
+		cudaStreamDestroy(p->copy_stream);
 	if (p->stream)
 		cudaStreamDestroy(p->stream);
 	delete p;
