@@ -200,6 +200,25 @@ def run_ours(args):
     ms_per_step = ms_total / args.steps
     value = rays_per_step / ms_per_step / 1e3            # Mrays/s, whole job
     value_lod = rays_per_step / (ms_lod / args.steps) / 1e3
+    # LOD + beam pre-pass (the reference's optional BEAM_OPTIMIZATION path, row N3); single-GPU frames only
+    value_lod_beam = None
+    if n == 1:
+        beam_buf = torch.zeros(((GW + 7) // 8) * ((GH + 7) // 8), dtype=torch.float32, device="cuda")
+        ev = []
+        with torch.cuda.stream(stream):
+            for s in range(-1, args.steps):
+                P = camera(cfg, root, s + 1000, GW, GH, True)
+                B = abi.beam_params(P)
+                flush.fill_(s & 0xFF)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                pool.BeamDev(B, beam_buf.data_ptr())
+                pool.TraceBeamDev(P, beam_buf.data_ptr(), B.width, B.height, rgba8=rgba.data_ptr())
+                e1.record()
+                if s >= 0:
+                    ev.append((e0, e1))
+            torch.cuda.synchronize()
+        value_lod_beam = rays_per_step / (sum(a_.elapsed_time(b_) for a_, b_ in ev) / args.steps) / 1e3
 
     # ---- e2e: through the C ABI with HOST buffers, wall clock incl. the copies ----
     # Every step passes the 84-byte parameter block in and reads the shaded frame (rgba8) back into pinned host
@@ -285,7 +304,8 @@ def run_ours(args):
                        "pool_used_MB": round(pool.UsedWords() * 4 / 1e6, 1),
                        "l2": "flushed between steps (256 MB fill outside the timed events); pool 800 MB > 126 MB L2",
                        "parallelism": f"screen-tile shard x{n}, replicated pool" if n > 1 else "single GPU"},
-            "value_lod": round(value_lod, 2), "wall_s_timed_region": round(wall, 4),
+            "value_lod": round(value_lod, 2), "value_lod_beam": round(value_lod_beam, 2) if value_lod_beam else None,
+            "wall_s_timed_region": round(wall, 4),
             "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": 84,
                     "d2h_bytes_per_step": int(local_px * 4 * n), "frame_checksum": checksum,
                     "value_blocking_call": round(e2e_sync_value, 2),

@@ -189,6 +189,16 @@ hd_status hd_trace_tiles(hd_pool *pool, const hd_trace_params *params, const hd_
                          const hd_trace_outputs *host_out);
 hd_status hd_trace_tiles_dev(hd_pool *pool, const hd_trace_params *params, const hd_tile_shard *shard,
                              const hd_trace_outputs *dev_out);
+/* Beam optimisation (row N3): replaces BeamPass::CmdExecute + shader/src/beam.frag (src/rg/BeamPass.cpp:81-111) and
+ * trace.frag compiled with BEAM_OPTIMIZATION (trace.frag:384-389).  beam_params is the beam pass's own block: same
+ * camera, width/height = ceil(W/8) x ceil(H/8), proj_factor with the 8-pixel tolerance.  hd_beam_dev writes the
+ * coarse start-t image (float, +inf = miss); hd_trace_with_beam* start every ray at 0.98 x the minimum of the 2x2
+ * beam texels around the pixel.  host_beam (may be NULL) receives the beam image. */
+hd_status hd_beam_dev(hd_pool *pool, const hd_trace_params *beam_params, float *beam_dev);
+hd_status hd_trace_with_beam_dev(hd_pool *pool, const hd_trace_params *params, const float *beam_dev, uint32_t beam_w,
+                                 uint32_t beam_h, const hd_trace_outputs *dev_out);
+hd_status hd_trace_with_beam(hd_pool *pool, const hd_trace_params *params, const hd_trace_params *beam_params,
+                             const hd_trace_outputs *host_out, float *host_beam);
 /* Pipelined frames: submit enqueues the trace of one frame and the asynchronous copy of its shaded rgba8 plane into
  * host_rgba8 (pinned host memory for full overlap) on a copy stream; collect blocks until that frame has landed.
  * Two slots (0/1) may be in flight, so the read-back of frame k overlaps the trace of frame k+1 (a frame loop with

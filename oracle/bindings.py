@@ -84,6 +84,10 @@ class Oracle(_Lib):
         L.orc_traverse.argtypes = [pu32, u32, u32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.orc_trace_frame.restype = u64
         L.orc_trace_frame.argtypes = [pu32, pu32, pu32, C.POINTER(HdTraceParams), u32, u32, u32, u32, pu32, vp, pu32]
+        L.orc_trace_frame_beam.restype = u64
+        L.orc_trace_frame_beam.argtypes = [pu32, pu32, pu32, C.POINTER(HdTraceParams), u32, u32, u32, u32, pu32, vp, pu32,
+                                           C.POINTER(C.c_float), u32, u32]
+        L.orc_beam_frame.argtypes = [pu32, C.POINTER(HdTraceParams), C.POINTER(C.c_float)]
         L.orc_trace_frame_host.restype = u64
         L.orc_trace_frame_host.argtypes = [pu32, u32, C.POINTER(HdTraceParams), u32, u32, u32, u32, C.POINTER(C.c_uint8),
                                            C.POINTER(C.c_float)]
@@ -121,8 +125,14 @@ class Oracle(_Lib):
         hit = self.lib.orc_traverse(words_ptr, node_levels, root, o3, d3, out)
         return (np.array(out[:], dtype=np.float32) if hit else None)
 
+    def beam_frame(self, words_ptr, beam_params):
+        """beam.frag over the beam image described by beam_params (abi.beam_params); float32 [bh, bw]."""
+        out = np.zeros((beam_params.height, beam_params.width), np.float32)
+        self.lib.orc_beam_frame(words_ptr, C.byref(beam_params), out.ctypes.data_as(C.POINTER(C.c_float)))
+        return out
+
     def trace_frame(self, words_ptr, params, color_nodes=None, color_leaves=None, rows=None, row_step=1,
-                    threads=None, want=("rgba8", "hits", "iters")):
+                    threads=None, want=("rgba8", "hits", "iters"), beam=None):
         W, H = params.width, params.height
         r0, r1 = rows if rows else (0, H)
         threads = threads or os.cpu_count()
@@ -133,8 +143,13 @@ class Oracle(_Lib):
         cl = color_leaves if color_leaves is not None else np.zeros(8, np.uint32)
         cnp = cn if isinstance(cn, C.POINTER(C.c_uint32)) else _u32p(cn)
         clp = cl if isinstance(cl, C.POINTER(C.c_uint32)) else _u32p(cl)
-        fetches = self.lib.orc_trace_frame(words_ptr, cnp, clp, C.byref(params), r0, r1, row_step, threads,
-                                           _u32p(rgba), hits.ctypes.data if hits is not None else None, _u32p(iters))
+        bp, bw, bh = None, 0, 0
+        if beam is not None:
+            beam = np.ascontiguousarray(beam, dtype=np.float32)
+            bp, bw, bh = beam.ctypes.data_as(C.POINTER(C.c_float)), beam.shape[1], beam.shape[0]
+        fetches = self.lib.orc_trace_frame_beam(words_ptr, cnp, clp, C.byref(params), r0, r1, row_step, threads,
+                                                _u32p(rgba), hits.ctypes.data if hits is not None else None, _u32p(iters),
+                                                bp, bw, bh)
         return {"rgba8": rgba, "hits": hits, "iters": iters, "fetches": fetches}
 
     def trace_frame_host(self, words_ptr, node_levels, params, rows=None, row_step=1, threads=None, want_pos=True):

@@ -469,6 +469,8 @@ struct Scene {
 	const uint32_t *nodes;
 	const uint32_t *color_nodes;
 	const uint32_t *color_leaves;
+	const float *beam = nullptr; // BEAM_OPTIMIZATION: coarse start-t image (beam.frag), bw x bh texels
+	uint32_t bw = 0, bh = 0;
 };
 
 struct March {
@@ -733,7 +735,23 @@ void shade_pixel(const Scene &s, const hd_trace_params &P, uint32_t px, uint32_t
 
 	March m{};
 	bool hit = false;
-	if (P.dag_root != kNull) {
+	bool marched = P.dag_root != kNull;
+	if (s.beam) { // trace.frag:384-389 — MIN-reduction linear sampler = min of the 2x2 texel footprint, x0.98
+		const float u = (float(px) + 0.5f) / float(P.width) * float(s.bw) - 0.5f;
+		const float w = (float(py) + 0.5f) / float(P.height) * float(s.bh) - 0.5f;
+		int i0 = int(std::floor(u)), j0 = int(std::floor(w));
+		int i1 = std::min(i0 + 1, int(s.bw) - 1), j1 = std::min(j0 + 1, int(s.bh) - 1);
+		i0 = std::max(i0, 0), j0 = std::max(j0, 0);
+		float beam = fmin2(fmin2(s.beam[size_t(j0) * s.bw + i0], s.beam[size_t(j0) * s.bw + i1]),
+		                   fmin2(s.beam[size_t(j1) * s.bw + i0], s.beam[size_t(j1) * s.bw + i1]));
+		beam = beam * 0.98f;
+		marched = marched && !std::isinf(beam);
+		if (marched) {
+			const float o2[3] = {P.pos[0] + beam * d[0], P.pos[1] + beam * d[1], P.pos[2] + beam * d[2]};
+			march(s.nodes, P.dag_root, P.dag_leaf_level, true, P.proj_factor, beam, o2, d, m);
+			hit = m.hit;
+		}
+	} else if (marched) {
 		march(s.nodes, P.dag_root, P.dag_leaf_level, true, P.proj_factor, 0.0f, P.pos, d, m);
 		hit = m.hit;
 	}
@@ -741,7 +759,7 @@ void shade_pixel(const Scene &s, const hd_trace_params &P, uint32_t px, uint32_t
 	out.rec = {{0, 0, 0}, 0};
 	float norm[3] = {0, 0, 0};
 	uint32_t vox[3] = {0, 0, 0}, vox_size_log2 = 0;
-	if (P.dag_root != kNull) {
+	if (marched) {
 		// normal, trace.frag:223-234
 		float tcn[3];
 		for (int i = 0; i < 3; ++i)
@@ -1010,10 +1028,45 @@ int orc_traverse(const uint32_t *words, uint32_t node_levels, uint32_t root, con
 
 // Frame trace — trace.frag main() for rows [row_begin,row_end) step row_step, n_threads workers (rows interleaved).
 // Outputs are full-frame row-major planes (any may be NULL); returns the number of 32-bit words fetched (F·rays).
+uint64_t orc_trace_frame_beam(const uint32_t *nodes, const uint32_t *color_nodes, const uint32_t *color_leaves,
+                              const hd_trace_params *P, uint32_t row_begin, uint32_t row_end, uint32_t row_step,
+                              uint32_t n_threads, uint32_t *rgba8, hd_hit_record *hits, uint32_t *iters, const float *beam,
+                              uint32_t bw, uint32_t bh);
 uint64_t orc_trace_frame(const uint32_t *nodes, const uint32_t *color_nodes, const uint32_t *color_leaves,
                          const hd_trace_params *P, uint32_t row_begin, uint32_t row_end, uint32_t row_step,
                          uint32_t n_threads, uint32_t *rgba8, hd_hit_record *hits, uint32_t *iters) {
-	Scene s{nodes, color_nodes, color_leaves};
+	return orc_trace_frame_beam(nodes, color_nodes, color_leaves, P, row_begin, row_end, row_step, n_threads, rgba8, hits,
+	                            iters, nullptr, 0, 0);
+}
+
+// Coarse beam image — shader/src/beam.frag:59-223 with the parameter block of src/rg/BeamPass.cpp:81-111
+// (width/height = beam image size, proj_factor = the pass's own).  out[bw*bh] floats, +inf where the beam misses.
+void orc_beam_frame(const uint32_t *nodes, const hd_trace_params *B, float *out) {
+	for (uint32_t y = 0; y < B->height; ++y)
+		for (uint32_t x = 0; x < B->width; ++x) {
+			float cx = (float(x) + 0.5f) / float(B->width), cy = (float(y) + 0.5f) / float(B->height);
+			cx = cx * 2.0f - 1.0f, cy = cy * 2.0f - 1.0f;
+			float d[3];
+			for (int i = 0; i < 3; ++i)
+				d[i] = (B->look[i] - B->side[i] * cx) - B->up[i] * cy;
+			normalize3(d);
+			float t = fbits(0x7F800000u);
+			if (B->dag_root != kNull) {
+				March m{};
+				march(nodes, B->dag_root, B->dag_leaf_level, true, B->proj_factor, 0.0f, B->pos, d, m);
+				if (m.hit)
+					t = fmax2(m.t_min - m.scale_exp2, 0.0f); // beam.frag:219
+			}
+			out[size_t(y) * B->width + x] = t;
+		}
+}
+
+// trace.frag compiled with BEAM_OPTIMIZATION (beam == NULL: the plain shader)
+uint64_t orc_trace_frame_beam(const uint32_t *nodes, const uint32_t *color_nodes, const uint32_t *color_leaves,
+                              const hd_trace_params *P, uint32_t row_begin, uint32_t row_end, uint32_t row_step,
+                              uint32_t n_threads, uint32_t *rgba8, hd_hit_record *hits, uint32_t *iters, const float *beam,
+                              uint32_t bw, uint32_t bh) {
+	Scene s{nodes, color_nodes, color_leaves, beam, bw, bh};
 	std::atomic<uint64_t> total{0};
 	if (n_threads == 0)
 		n_threads = 1;

@@ -140,3 +140,30 @@ def test_pipelined_frames_equal_blocking_frames(oracle, hd):
             exp = want[i].reshape(-1) if shard is None else dev.Trace(P, want=("rgba8",), shard=shard)["rgba8"]
             assert np.array_equal(got[i], exp), (i, shard)
     dev.close()
+
+
+def test_beam_prepass_and_beam_trace(oracle, hd):
+    """Row N3: beam.frag pre-pass and trace.frag with BEAM_OPTIMIZATION, bit-exact against their restatement;
+    the beam-optimised frame equals the plain frame wherever both hit (the beam is conservative)."""
+    cfg = abi.default_config(level_count=10, top_level_count=9)
+    opool = oracle.pool(cfg)
+    root = opool.edit_batch(NULL, [abi.terrain(cfg.voxel_level)] + abi.random_spheres(60, cfg.voxel_level, seed=9, rmin=8, rmax=60))
+    dev = hd.DAGNodePool(cfg)
+    dev.UploadFrom(opool)
+    W, H = 645, 363   # not multiples of 8: partial beam texels
+    for cam in (((0.5, 0.75, 0.5), 0.6, -0.5236), ((0.1, 0.6, 0.9), 2.3, -0.2), ((0.5, 1.05, 0.5), 0.0, -1.4)):
+        P = abi.camera_params(cfg, root, *cam, W, H, color_root=(1 << 30) | 0x3377AA)
+        B = abi.beam_params(P)
+        assert (B.width, B.height) == ((W + 7) // 8, (H + 7) // 8)
+        exp_beam = oracle.beam_frame(opool.words_ptr, B)
+        exp = oracle.trace_frame(opool.words_ptr, P, beam=exp_beam)
+        got = dev.TraceBeam(P, B)
+        assert np.array_equal(got["beam"].view(np.uint32), exp_beam.view(np.uint32))
+        for k in ("hits", "iters", "rgba8"):
+            assert np.array_equal(got[k], exp[k]), (k, cam)
+        plain = dev.Trace(P)
+        assert plain["iters"].sum() > got["iters"].sum()          # fewer iterations: that is the optimisation
+        both = (plain["hits"]["packed"] >> 31 == 1) & (got["hits"]["packed"] >> 31 == 1)
+        same = (plain["hits"]["packed"] == got["hits"]["packed"]) & (plain["hits"]["vox"] == got["hits"]["vox"]).all(-1)
+        assert both.sum() > 1000 and same[both].mean() > 0.98      # LOD bias differs by the beam term on a few pixels
+    dev.close()

@@ -175,3 +175,13 @@ def camera_params(cfg, root, pos, yaw, pitch, width, height, fov=np.pi / 3, colo
     return P
 
 
+def beam_params(P, fov=np.pi / 3):
+    """Parameter block of the beam pre-pass for a frame P (src/rg/BeamPass.cpp:11-17,81-111): same camera, image of
+    ceil(W/8) x ceil(H/8) texels, projection factor with the 8-pixel screen tolerance (float32 host maths)."""
+    f = np.float32
+    B = HdTraceParams.from_buffer_copy(P)
+    B.width, B.height = (P.width + 7) // 8, (P.height + 7) // 8
+    inv_2tan = f(1.0) / (f(2.0) * f(np.tan(f(0.5) * f(fov))))
+    tol = f(1.0) / (f(P.height) / f(8.0))
+    B.proj_factor = float(inv_2tan / tol)
+    return B

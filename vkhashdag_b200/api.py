@@ -61,7 +61,8 @@ SYMBOLS = [
     "hd_upsert_nodes", "hd_color_upload", "hd_trace", "hd_trace_dev", "hd_trace_tiles", "hd_trace_tiles_dev",
     "hd_tile_shard_pixels", "hd_traverse_ray", "hd_dirty_count", "hd_dirty_ranges", "hd_dirty_pack_dev",
     "hd_dirty_apply_dev", "hd_dirty_reset", "hd_pool_used_words", "hd_sync", "hd_kernel_launches", "hd_pool_save",
-    "hd_pool_load", "hd_gc", "hd_trace_submit", "hd_trace_collect",
+    "hd_pool_load", "hd_gc", "hd_trace_submit", "hd_trace_collect", "hd_beam_dev",
+    "hd_trace_with_beam_dev", "hd_trace_with_beam",
 ]
 
 
@@ -109,6 +110,9 @@ def lib():
     L.hd_trace_dev.argtypes = [vp, C.POINTER(HdTraceParams), C.POINTER(HdTraceOutputs)]
     L.hd_trace_tiles.argtypes = [vp, C.POINTER(HdTraceParams), C.POINTER(HdTileShard), C.POINTER(HdTraceOutputs)]
     L.hd_trace_tiles_dev.argtypes = [vp, C.POINTER(HdTraceParams), C.POINTER(HdTileShard), C.POINTER(HdTraceOutputs)]
+    L.hd_beam_dev.argtypes = [vp, C.POINTER(HdTraceParams), vp]
+    L.hd_trace_with_beam_dev.argtypes = [vp, C.POINTER(HdTraceParams), vp, u32, u32, C.POINTER(HdTraceOutputs)]
+    L.hd_trace_with_beam.argtypes = [vp, C.POINTER(HdTraceParams), C.POINTER(HdTraceParams), C.POINTER(HdTraceOutputs), vp]
     L.hd_trace_submit.argtypes = [vp, C.POINTER(HdTraceParams), C.POINTER(HdTileShard), vp, u32]
     L.hd_trace_collect.argtypes = [vp, u32]
     L.hd_tile_shard_pixels.restype = u64
@@ -344,6 +348,25 @@ class DAGNodePool:
         else:
             shard = HdTileShard(*shard) if not isinstance(shard, HdTileShard) else shard
             _check(self._L.hd_trace_tiles_dev(self._h, C.byref(params), C.byref(shard), C.byref(o)))
+
+    def TraceBeam(self, params, beam_params, want=("rgba8", "hits", "iters")):
+        """Beam pre-pass + beam-optimised trace (BeamPass + trace.frag with BEAM_OPTIMIZATION), host outputs.
+        Returns the planes plus 'beam' (float32 [bh, bw])."""
+        shape = (params.height, params.width)
+        res = {"beam": np.zeros((beam_params.height, beam_params.width), np.float32)}
+        for name, dt in (("rgba8", np.uint32), ("hits", HIT_DTYPE), ("iters", np.uint32), ("fetches", np.uint32)):
+            if name in want:
+                res[name] = np.zeros(shape, dt)
+        o = HdTraceOutputs(*[res[n].ctypes.data if n in res else None for n in ("rgba8", "hits", "iters", "fetches")])
+        _check(self._L.hd_trace_with_beam(self._h, C.byref(params), C.byref(beam_params), C.byref(o), res["beam"].ctypes.data))
+        return res
+
+    def BeamDev(self, beam_params, beam_dev_ptr):
+        _check(self._L.hd_beam_dev(self._h, C.byref(beam_params), beam_dev_ptr))
+
+    def TraceBeamDev(self, params, beam_dev_ptr, bw, bh, rgba8=0, hits=0, iters=0):
+        o = HdTraceOutputs(rgba8 or None, hits or None, iters or None, None)
+        _check(self._L.hd_trace_with_beam_dev(self._h, C.byref(params), beam_dev_ptr, bw, bh, C.byref(o)))
 
     def TraceSubmit(self, params, host_rgba8, slot, shard=None):
         """hd_trace_submit: enqueue one frame + async read-back of its rgba8 plane into a host array (numpy, ideally
