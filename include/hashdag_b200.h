@@ -176,9 +176,26 @@ hd_status hd_upsert_nodes(hd_pool *pool, uint32_t level, const uint32_t *nodes, 
                           uint32_t *out_ptrs);
 
 /* ---- colour pool: the DAGColorPool buffers the tracer reads (src/DAGColorPool.hpp:43-52; bindings 1,2 of
- *      shader/src/trace.frag:6-7).  Mutation on the GPU is a "next" row. ---- */
+ *      shader/src/trace.frag:6-7). ---- */
 hd_status hd_color_upload(hd_pool *pool, const uint32_t *color_nodes, uint64_t node_words, const uint32_t *color_leaves,
                           uint64_t leaf_words);
+
+/* Colour pool state and colour-aware edits on the GPU (row N2).  hd_color_config tells the pool the colour leaf level
+ * (DAGColorPool::Config::leaf_level, src/main.cpp:204-211) and the current colour root (DAGColorPool::SetRoot).
+ * hd_edit_color replaces vbr_edit(...) of src/main.cpp:224-230 for the editors the reference ships:
+ *   edit->kind == HD_EDIT_AABB_FILL                      AABBEditor with a colour        (main.cpp:47-69)
+ *   edit->kind == HD_EDIT_SPHERE_FILL, paint == 0        SphereEditor<kFill>             (main.cpp:107-149)
+ *   edit->kind == HD_EDIT_SPHERE_FILL, paint != 0        SphereEditor<kPaint> (geometry untouched)
+ * It performs the geometry edit AND the colour update (VBREditorWrapper, include/hashdag/VBREditor.hpp:26-107; leaf
+ * chunks as VBRChunkWriter would emit them, VBRColor.hpp:368-487; SetNode/FillNode/SetLeaf, src/DAGColorPool.hpp:147-204)
+ * and returns both new roots.  rgb8 = 0xBBGGRR.  hd_color_read copies the buffers back (sizes from hd_color_sizes). */
+hd_status hd_color_config(hd_pool *pool, uint32_t leaf_level, uint32_t color_root);
+uint32_t hd_color_root(const hd_pool *pool);
+uint32_t hd_color_leaf_level(const hd_pool *pool);
+hd_status hd_color_sizes(hd_pool *pool, uint64_t *node_words, uint64_t *leaf_words);
+hd_status hd_color_read(hd_pool *pool, uint32_t *nodes, uint64_t node_words, uint32_t *leaves, uint64_t leaf_words);
+hd_status hd_edit_color(hd_pool *pool, uint32_t root_in, const hd_edit_desc *edit, uint32_t rgb8, uint32_t paint,
+                        uint32_t *root_out, uint32_t *color_root_out, hd_edit_stats *stats);
 
 /* ---- trace: replaces TracePass::CmdExecute + shader/src/trace.frag main() (TracePass.cpp:106-139) ----
  * Outputs are HOST pointers (copied back inside the call) for hd_trace / hd_trace_tiles and DEVICE pointers for

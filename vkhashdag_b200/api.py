@@ -62,7 +62,8 @@ SYMBOLS = [
     "hd_tile_shard_pixels", "hd_traverse_ray", "hd_dirty_count", "hd_dirty_ranges", "hd_dirty_pack_dev",
     "hd_dirty_apply_dev", "hd_dirty_reset", "hd_pool_used_words", "hd_sync", "hd_kernel_launches", "hd_pool_save",
     "hd_pool_load", "hd_gc", "hd_trace_submit", "hd_trace_collect", "hd_beam_dev",
-    "hd_trace_with_beam_dev", "hd_trace_with_beam",
+    "hd_trace_with_beam_dev", "hd_trace_with_beam", "hd_color_config", "hd_color_root", "hd_color_leaf_level",
+    "hd_color_sizes", "hd_color_read", "hd_edit_color",
 ]
 
 
@@ -110,6 +111,14 @@ def lib():
     L.hd_trace_dev.argtypes = [vp, C.POINTER(HdTraceParams), C.POINTER(HdTraceOutputs)]
     L.hd_trace_tiles.argtypes = [vp, C.POINTER(HdTraceParams), C.POINTER(HdTileShard), C.POINTER(HdTraceOutputs)]
     L.hd_trace_tiles_dev.argtypes = [vp, C.POINTER(HdTraceParams), C.POINTER(HdTileShard), C.POINTER(HdTraceOutputs)]
+    L.hd_color_config.argtypes = [vp, u32, u32]
+    L.hd_color_root.restype = u32
+    L.hd_color_root.argtypes = [vp]
+    L.hd_color_leaf_level.restype = u32
+    L.hd_color_leaf_level.argtypes = [vp]
+    L.hd_color_sizes.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.hd_color_read.argtypes = [vp, vp, u64, vp, u64]
+    L.hd_edit_color.argtypes = [vp, u32, C.POINTER(HdEditDesc), u32, u32, pu32, pu32, C.POINTER(HdEditStats)]
     L.hd_beam_dev.argtypes = [vp, C.POINTER(HdTraceParams), vp]
     L.hd_trace_with_beam_dev.argtypes = [vp, C.POINTER(HdTraceParams), vp, u32, u32, C.POINTER(HdTraceOutputs)]
     L.hd_trace_with_beam.argtypes = [vp, C.POINTER(HdTraceParams), C.POINTER(HdTraceParams), C.POINTER(HdTraceOutputs), vp]
@@ -310,6 +319,31 @@ class DAGNodePool:
         n = np.ascontiguousarray(color_nodes, dtype=np.uint32)
         l = np.ascontiguousarray(color_leaves, dtype=np.uint32)
         _check(self._L.hd_color_upload(self._h, n.ctypes.data, n.size, l.ctypes.data, l.size))
+
+    # -- colour pool (DAGColorPool) --
+    def ColorConfig(self, leaf_level, color_root=COLOR_NULL):
+        """DAGColorPool::Config::leaf_level + SetRoot (src/main.cpp:204-211, DAGColorPool.hpp:209)."""
+        _check(self._L.hd_color_config(self._h, leaf_level, color_root))
+
+    def ColorRoot(self):
+        return self._L.hd_color_root(self._h)
+
+    def ReadColor(self):
+        """(color_nodes, color_leaves) numpy copies of the used parts of the two colour buffers."""
+        n, l = C.c_uint64(), C.c_uint64()
+        _check(self._L.hd_color_sizes(self._h, C.byref(n), C.byref(l)))
+        nodes, leaves = np.zeros(max(n.value, 8), np.uint32), np.zeros(max(l.value, 8), np.uint32)
+        _check(self._L.hd_color_read(self._h, nodes.ctypes.data, n.value, leaves.ctypes.data, l.value))
+        return nodes, leaves
+
+    def EditColor(self, root, editor, rgb8, paint=False):
+        """vbr_edit(editor) of src/main.cpp:224-230: geometry edit + colour update on the GPU.  Returns
+        (new node root, new colour root)."""
+        d = _desc(editor)
+        out, cout, st = C.c_uint32(root), C.c_uint32(), HdEditStats()
+        _check(self._L.hd_edit_color(self._h, root, C.byref(d), rgb8, int(paint), C.byref(out), C.byref(cout), C.byref(st)))
+        self.last_stats = st.as_dict()
+        return out.value, cout.value
 
     # -- trace --
     def Trace(self, params, want=("rgba8", "hits", "iters"), shard=None, out=None):

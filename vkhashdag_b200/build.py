@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libhashdag_b200.so")
-SOURCES = ["pool.cu", "trace.cu", "edit.cu", "sync.cu", "gc.cu"]
+SOURCES = ["pool.cu", "trace.cu", "edit.cu", "sync.cu", "gc.cu", "color.cu"]
 # trace.cu: -fmad=false — bit-exact fp32 parity with the reference arithmetic evaluated without contraction
 EXTRA = {"trace.cu": ["-fmad=false"]}
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -1,0 +1,779 @@
+// color.cu — device colour pool and colour-aware edits on the GPU.
+//
+// Replaces, for the editors the reference ships (AABBEditor, SphereEditor<kFill>, SphereEditor<kPaint>,
+// src/main.cpp:32-150), the colour side of an edit: VBREditorWrapper (include/hashdag/VBREditor.hpp:26-107) threading a
+// colour-octree pointer and a VBRChunkWriter (VBRColor.hpp:368-487) through the edit recursion, and DAGColorPool's
+// SetNode / FillNode / SetLeaf (src/DAGColorPool.hpp:147-204).  Word layout is the reference's.
+//
+// The reference rewrites each touched colour leaf as a sequential Morton-order stream.  Here the stream is never
+// materialised sequentially: the colour every voxel of a touched leaf ends up with is a pure function of the OLD
+// geometry path above it, the old colour chunk and the editor (k_voxels walks that chain per voxel), and the chunk
+// the writer would have produced is the canonical run-length encoding of that colour sequence (a block starts where
+// (colors, bits_per_weight) changes or a 2^14-voxel macro block starts — VBRChunkWriter::append, VBRColor.hpp:384-409),
+// which two prefix sums and one emit kernel produce in parallel.  Above the colour-leaf level the octree is rebuilt
+// level-synchronously (k_cdown / k_cup) with SetNode's collapse rules.
+#include "common.cuh"
+#include "editors.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace hd {
+
+constexpr int kCB = 256;
+constexpr uint32_t kTagNode = 0u, kTagColor = 1u, kTagLeaf = 2u, kTagNull = 3u; // src/DAGColorPool.hpp:26
+constexpr uint32_t kMacroBits = 14u;                                          // VBRColor.hpp:46-49
+constexpr uint32_t kCPending = 0xFFFFFFFEu; // not a valid pointer: tag 3 with data != 0 never occurs otherwise
+
+__device__ __forceinline__ uint32_t ctag(uint32_t p) { return p >> 30; }
+__device__ __forceinline__ uint32_t cdata(uint32_t p) { return p & 0x3FFFFFFFu; }
+
+// FillNode stores RGB8Color{color.Get()}: u8 -> float/255 -> *255 -> truncation (Color.hpp:20-25, DAGColorPool.hpp:165-167)
+__host__ __device__ inline uint32_t fill_node_rgb8(uint32_t rgb8) {
+	uint32_t out = 0;
+	for (int i = 0; i < 3; ++i) {
+		const float f = float((rgb8 >> (8 * i)) & 0xFFu) / 255.0f;
+		out |= (uint32_t(uint8_t(f * 255.0f)) & 0xFFu) << (8 * i);
+	}
+	return out;
+}
+
+struct ColorEdit {
+	hd_edit_desc d;
+	uint32_t rgb8;    // editor colour (VBRColor{RGB8Color}: colors = rgb8, bits_per_weight = 0)
+	uint32_t paint;   // SphereEditor<kPaint>
+	uint32_t voxel_level, node_levels, leaf_level;
+};
+
+// Editor::EditNode(config, coord, ptr, VBRColor &final_color) of src/main.cpp:47-56,107-126.
+// fill = GetFill(octree pointer): has_fill / fill_rgb8.  Returns the edit type; color_set = "final_color has a value".
+__device__ inline EditType color_edit_node(const ColorEdit &e, uint32_t bits, uint32_t x, uint32_t y, uint32_t z, bool ptr_null,
+                                           bool has_fill, uint32_t fill_rgb8, bool &color_set) {
+	EditType t = edit_node(e.d, bits, x, y, z);
+	const bool same = has_fill && fill_rgb8 == e.rgb8;
+	if (e.paint) {
+		if (t == kFill) {
+			color_set = true;
+			t = kNotAffected;
+		} else
+			color_set = ptr_null || same;
+		if (ptr_null)
+			t = kNotAffected;
+	} else
+		color_set = t == kFill || ptr_null || same;
+	return t;
+}
+
+// raw colour of voxel `m` (Morton index inside the colour leaf) in the chunk at `idx` — the lookup of trace.frag:304-349
+// without the decode: colors word, bits per weight, weight.
+__device__ inline void chunk_lookup(const uint32_t *__restrict__ lv, uint32_t idx, uint32_t m, uint32_t &colors, uint32_t &bpw,
+                                    uint32_t &weight) {
+	const uint32_t macro_cnt = lv[idx + 1], block_cnt_all = lv[idx + 2];
+	const uint32_t macro_off = idx + 4, block_base = macro_off + (macro_cnt << 1), weight_off = block_base + (block_cnt_all << 1);
+	const uint32_t macro_id = m >> kMacroBits;
+	const uint32_t mx = lv[macro_off + (macro_id << 1)], my = lv[macro_off + (macro_id << 1) + 1];
+	uint32_t block_off = block_base + (mx << 1);
+	uint32_t block_cnt = macro_id + 1 < macro_cnt ? lv[macro_off + ((macro_id + 1) << 1)] - mx : block_cnt_all - mx;
+	const uint32_t vid = m & ((1u << kMacroBits) - 1u);
+	while (block_cnt) { // first block with voxel_index_offset > vid
+		const uint32_t step = block_cnt >> 1;
+		if ((lv[block_off + (step << 1) + 1] >> 18) <= vid)
+			block_cnt -= step + 1, block_off += (step + 1) << 1;
+		else
+			block_cnt = step;
+	}
+	block_off -= 2;
+	const uint32_t bx = lv[block_off], by = lv[block_off + 1];
+	colors = bx, bpw = (by >> 16) & 3u, weight = 0;
+	if (bpw) {
+		const uint32_t bit = my + (by & 0xFFFFu) + (vid - (by >> 18)) * bpw, o = bit & 31u;
+		uint32_t w = lv[weight_off + (bit >> 5)] >> o;
+		if (o + bpw > 32)
+			w |= lv[weight_off + (bit >> 5) + 1] << (32u - o);
+		weight = w & ((1u << bpw) - 1u);
+	}
+}
+
+// ---- octree part (levels <= leaf_level): BFS work items ----------------------------------------------------------
+struct CItems {
+	uint32_t n, cap;
+	uint32_t *geom;   // old geometry pointer of the node
+	uint32_t *oct;    // colour-octree pointer of the node before the edit
+	uint64_t *pos;    // x | y<<21 | z<<42
+	uint32_t *parent; // (parent item << 3) | slot, 0xFFFFFFFF for the root
+	uint32_t *child;  // [n*8] resulting child pointers (inner items)
+	uint32_t *result; // resulting pointer of the item
+};
+
+__device__ __forceinline__ uint32_t oct_child(const uint32_t *__restrict__ cnodes, uint32_t p, uint32_t c) {
+	const uint32_t t = ctag(p); // DAGColorPool::GetChild, DAGColorPool.hpp:139-143
+	return t == kTagNode ? cnodes[(size_t(cdata(p)) << 3) | c] : (t == kTagColor ? p : HD_COLOR_NULL);
+}
+
+// classify one node of the octree part: returns 0 = final (ptr_out), 1 = becomes an inner item, 2 = becomes a leaf item
+__device__ inline int classify_oct(const ColorEdit &e, uint32_t level, uint32_t x, uint32_t y, uint32_t z, uint32_t geom,
+                                   uint32_t oct, uint32_t &ptr_out) {
+	const bool has_fill = ctag(oct) == kTagColor;
+	bool color_set;
+	const EditType t = color_edit_node(e, e.voxel_level - level, x, y, z, geom == kNull, has_fill, cdata(oct), color_set);
+	if (color_set) { // VBREditor.hpp:52-55: FillNode, final
+		ptr_out = (kTagColor << 30) | fill_node_rgb8(e.rgb8);
+		return 0;
+	}
+	if (t == kClear) { // VBREditor.hpp:56-57 (no colour editor returns kClear today; kept for completeness)
+		ptr_out = HD_COLOR_NULL;
+		return 0;
+	}
+	if (t == kProceed)
+		return level == e.leaf_level ? 2 : 1;
+	ptr_out = oct;
+	return 0;
+}
+
+__global__ void k_croot(ColorEdit e, uint32_t geom_root, uint32_t oct_root, CItems inner, CItems leaf, uint32_t *counts,
+                        uint32_t *root_out) {
+	if (threadIdx.x || blockIdx.x)
+		return;
+	uint32_t res = oct_root;
+	const int k = classify_oct(e, 0, 0, 0, 0, geom_root, oct_root, res);
+	if (k == 0) {
+		*root_out = res;
+		return;
+	}
+	CItems &dst = k == 1 ? inner : leaf;
+	counts[k - 1] = 1;
+	dst.geom[0] = geom_root, dst.oct[0] = oct_root, dst.pos[0] = 0, dst.parent[0] = 0xFFFFFFFFu;
+}
+
+// thread per (inner item at `level`, child): VBREditorWrapper::EditNode for levels <= leaf_level (VBREditor.hpp:37-59)
+__global__ void __launch_bounds__(kCB) k_cdown(ColorEdit e, uint32_t level, const uint32_t *__restrict__ words,
+                                               const uint32_t *__restrict__ cnodes, CItems in, CItems inner, CItems leaf,
+                                               uint32_t *counts) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, item = t >> 3, c = t & 7u;
+	if (item >= in.n)
+		return;
+	const uint32_t g = in.geom[item];
+	uint32_t child = kNull;
+	if (g != kNull) {
+		const uint32_t mask = words[g];
+		if (mask >> c & 1u)
+			child = words[g + 1u + __popc(mask & ((1u << c) - 1u))];
+	}
+	const uint32_t oct = oct_child(cnodes, in.oct[item], c);
+	const uint64_t p = in.pos[item];
+	const uint32_t x = ((uint32_t(p) & 0x1FFFFFu) << 1) | (c & 1u), y = ((uint32_t(p >> 21) & 0x1FFFFFu) << 1) | ((c >> 1) & 1u),
+	               z = ((uint32_t(p >> 42) & 0x1FFFFFu) << 1) | ((c >> 2) & 1u);
+	uint32_t res = oct;
+	const int k = classify_oct(e, level + 1u, x, y, z, child, oct, res);
+	if (k == 0) {
+		in.child[size_t(item) * 8u + c] = res;
+		return;
+	}
+	CItems &dst = k == 1 ? inner : leaf;
+	const uint32_t slot = atomicAdd(&counts[k - 1], 1u);
+	if (slot >= dst.cap) {
+		counts[3] = 1;
+		in.child[size_t(item) * 8u + c] = oct;
+		return;
+	}
+	dst.geom[slot] = child, dst.oct[slot] = oct;
+	dst.pos[slot] = uint64_t(x) | (uint64_t(y) << 21) | (uint64_t(z) << 42);
+	dst.parent[slot] = (item << 3) | c;
+	in.child[size_t(item) * 8u + c] = kCPending;
+}
+
+// JoinNode above the leaf level: DAGColorPool::SetNode (DAGColorPool.hpp:147-163).  Thread per inner item.
+__global__ void __launch_bounds__(kCB) k_cup(CItems it, uint32_t *cnodes, uint32_t *ctr, uint64_t node_cap, uint32_t *parent_child,
+                                             uint32_t *root_out) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= it.n)
+		return;
+	uint32_t ch[8];
+	bool all_null = true, all_same = true;
+	for (int c = 0; c < 8; ++c) {
+		ch[c] = it.child[size_t(i) * 8u + c];
+		all_null &= ctag(ch[c]) == kTagNull;
+		all_same &= ch[c] == ch[0];
+	}
+	const uint32_t old = it.oct[i];
+	uint32_t res;
+	if (all_null)
+		res = HD_COLOR_NULL;
+	else if (ctag(ch[0]) == kTagColor && all_same)
+		res = ch[0];
+	else {
+		bool same = ctag(old) == kTagNode;
+		if (same)
+			for (int c = 0; c < 8 && same; ++c)
+				same = cnodes[(size_t(cdata(old)) << 3) | c] == ch[c];
+		if (same)
+			res = old;
+		else {
+			const uint32_t id = atomicAdd(&ctr[0], 1u);
+			if ((uint64_t(id) + 1) * 8 > node_cap) {
+				ctr[2] = 1;
+				res = old; // out of space: keep the old pointer (DAGColorPool.hpp:161)
+			} else {
+				for (int c = 0; c < 8; ++c)
+					cnodes[(size_t(id) << 3) | c] = ch[c];
+				res = (kTagNode << 30) | id;
+			}
+		}
+	}
+	const uint32_t par = it.parent[i];
+	if (par == 0xFFFFFFFFu)
+		*root_out = res;
+	else
+		parent_child[par] = res;
+}
+
+// ---- leaf part: per-voxel colour, then canonical VBR encoding -------------------------------------------------------
+// thread per (leaf item, Morton index): the colour the reference's writer would emit for that voxel
+// (VBREditorWrapper::EditNode below the leaf level + EditVoxel, VBREditor.hpp:60-80; editors main.cpp:47-69,107-149).
+__global__ void __launch_bounds__(kCB) k_voxels(ColorEdit e, const uint32_t *__restrict__ words, const uint32_t *__restrict__ cleaves,
+                                                CItems leaf, uint32_t first_leaf, uint32_t n_leaves, uint32_t sbits,
+                                                uint32_t *colors, uint8_t *bw) {
+	const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+	const uint32_t li = uint32_t(t >> sbits), m = uint32_t(t & ((1ull << sbits) - 1ull));
+	if (li >= n_leaves)
+		return;
+	const uint32_t item = first_leaf + li;
+	const uint32_t oct = leaf.oct[item];
+	const bool has_fill = ctag(oct) == kTagColor, has_src = ctag(oct) == kTagLeaf;
+	const uint32_t fill_rgb8 = cdata(oct), src = cdata(oct);
+	const uint64_t p = leaf.pos[item];
+	uint32_t x = uint32_t(p) & 0x1FFFFFu, y = uint32_t(p >> 21) & 0x1FFFFFu, z = uint32_t(p >> 42) & 0x1FFFFFu;
+	uint32_t g = leaf.geom[item];
+	uint32_t out_c = 0, out_b = 0, out_w = 0;
+	bool done = false;
+	// geometry levels below the colour leaf: nodes at levels leaf_level+1 .. node_levels-1
+	for (uint32_t L = e.leaf_level + 1u; L < e.node_levels && !done; ++L) {
+		const uint32_t c = (m >> (3u * (e.voxel_level - L))) & 7u;
+		uint32_t child = kNull;
+		if (g != kNull) {
+			const uint32_t mask = words[g];
+			if (mask >> c & 1u)
+				child = words[g + 1u + __popc(mask & ((1u << c) - 1u))];
+		}
+		x = (x << 1) | (c & 1u), y = (y << 1) | ((c >> 1) & 1u), z = (z << 1) | ((c >> 2) & 1u);
+		bool color_set;
+		const EditType et = color_edit_node(e, e.voxel_level - L, x, y, z, child == kNull, has_fill, fill_rgb8, color_set);
+		if (color_set) { // writer->Push(color, subtree)
+			out_c = e.rgb8, done = true;
+		} else if (et != kProceed) { // writer->Copy(subtree, fill)
+			if (has_src)
+				chunk_lookup(cleaves, src, m, out_c, out_b, out_w);
+			else
+				out_c = has_fill ? fill_rgb8 : 0u;
+			done = true;
+		}
+		g = child;
+	}
+	if (!done) { // EditVoxel through writer->Edit (VBREditor.hpp:71-80; main.cpp:64-69,143-149)
+		const uint32_t i = m & 63u;
+		const uint32_t vx = (x << 2) | ((i >> 2) & 2u) | (i & 1u), vy = (y << 2) | ((i >> 3) & 2u) | ((i >> 1) & 1u),
+		               vz = (z << 2) | ((i >> 4) & 2u) | ((i >> 2) & 1u);
+		const bool voxel = (words[g + (i >> 5)] >> (i & 31u)) & 1u;
+		if (voxel_in_range(e.d, vx, vy, vz) || !voxel)
+			out_c = e.rgb8;
+		else if (has_src)
+			chunk_lookup(cleaves, src, m, out_c, out_b, out_w);
+		else
+			out_c = has_fill ? fill_rgb8 : 0u;
+	}
+	colors[t] = out_c;
+	bw[t] = uint8_t(out_b | (out_w << 2));
+}
+
+// block-start flags and weight bit counts (VBRChunkWriter::append: a block starts at a macro block or where
+// (colors, bits_per_weight) differ from the previous voxel)
+__global__ void __launch_bounds__(kCB) k_flags(const uint32_t *__restrict__ colors, const uint8_t *__restrict__ bw, uint64_t n,
+                                               uint32_t sbits, uint32_t *flag, uint32_t *bits) {
+	const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (t >= n)
+		return;
+	const uint32_t b = bw[t] & 3u;
+	const uint32_t m = uint32_t(t & ((1ull << sbits) - 1ull)); // Morton index inside the leaf (m == 0 starts a chunk)
+	bool start = (m & ((1u << kMacroBits) - 1u)) == 0u;
+	if (!start)
+		start = colors[t] != colors[t - 1] || b != (bw[t - 1] & 3u);
+	flag[t] = start ? 1u : 0u;
+	bits[t] = b;
+}
+
+// ---- exclusive prefix sum over u32 (three-kernel scan, 1024 elements per CTA) ----------------------------------------
+__global__ void __launch_bounds__(256) k_scan_block(const uint32_t *__restrict__ in, uint32_t *out, uint32_t *block_sums, uint64_t n) {
+	__shared__ uint32_t s[1024];
+	__shared__ uint32_t warp_sums[8];
+	const uint64_t base = uint64_t(blockIdx.x) * 1024u;
+	uint32_t v[4], sum = 0;
+	for (int k = 0; k < 4; ++k) {
+		const uint64_t i = base + threadIdx.x * 4u + k;
+		v[k] = i < n ? in[i] : 0u;
+		sum += v[k];
+	}
+	// exclusive scan of per-thread sums across the CTA
+	uint32_t incl = sum;
+	const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+		if (lane >= uint32_t(d))
+			incl += o;
+	}
+	if (lane == 31)
+		warp_sums[w] = incl;
+	__syncthreads();
+	uint32_t woff = 0;
+	for (uint32_t k = 0; k < w; ++k)
+		woff += warp_sums[k];
+	uint32_t run = woff + incl - sum;
+	for (int k = 0; k < 4; ++k) {
+		const uint64_t i = base + threadIdx.x * 4u + k;
+		if (i < n)
+			out[i] = run;
+		run += v[k];
+	}
+	if (threadIdx.x == 255 && block_sums)
+		block_sums[blockIdx.x] = run;
+	(void)s;
+}
+__global__ void __launch_bounds__(256) k_scan_add(uint32_t *out, const uint32_t *__restrict__ block_offsets, uint64_t n) {
+	const uint64_t i = uint64_t(blockIdx.x) * 1024u + threadIdx.x * 4u;
+	const uint32_t o = block_offsets[blockIdx.x];
+	for (int k = 0; k < 4; ++k)
+		if (i + k < n)
+			out[i + k] += o;
+}
+
+static hd_status exclusive_scan(hd_pool *p, const uint32_t *in, uint32_t *out, uint64_t n) {
+	if (n == 0)
+		return HD_OK;
+	const uint64_t blocks = (n + 1023) / 1024;
+	uint32_t *sums = nullptr;
+	HD_CUDA_TRY(cudaMallocAsync(&sums, std::max<uint64_t>(blocks, 1) * 4, p->stream));
+	k_scan_block<<<uint32_t(blocks), 256, 0, p->stream>>>(in, out, sums, n);
+	HD_LAUNCH_CHECK();
+	if (blocks > 1) {
+		hd_status s = exclusive_scan(p, sums, sums, blocks);
+		if (s != HD_OK)
+			return s;
+		k_scan_add<<<uint32_t(blocks), 256, 0, p->stream>>>(out, sums, n);
+		HD_LAUNCH_CHECK();
+	}
+	HD_CUDA_TRY(cudaFreeAsync(sums, p->stream));
+	return HD_OK;
+}
+
+// words each leaf of the batch may have to append (0 when it will be rewritten in place); summed into *total
+__global__ void k_leaf_size(CItems leaf, uint32_t first_leaf, uint32_t n_leaves, uint32_t sbits, const uint32_t *__restrict__ flag,
+                            const uint32_t *__restrict__ fscan, const uint32_t *__restrict__ bits, const uint32_t *__restrict__ bscan,
+                            const uint32_t *__restrict__ cleaves, unsigned long long *total) {
+	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+	if (li >= n_leaves)
+		return;
+	const uint64_t S = 1ull << sbits, a = uint64_t(li) << sbits, last = a + S - 1;
+	const uint32_t block_cnt = fscan[last] + flag[last] - fscan[a], total_bits = bscan[last] + bits[last] - bscan[a];
+	const uint32_t data = uint32_t((S + (1u << kMacroBits) - 1u) >> kMacroBits) * 2u + block_cnt * 2u + ((total_bits + 31u) >> 5) + 4u;
+	uint32_t append = (data & 1u) ? data + 1u : data;
+	const uint32_t old = leaf.oct[first_leaf + li];
+	if (ctag(old) == kTagLeaf) {
+		const uint32_t block = cleaves[cdata(old)];
+		append = data <= block ? 0u : max(block << 1, append);
+	}
+	if (append)
+		atomicAdd(total, (unsigned long long)append);
+}
+
+// per leaf: sizes, allocation (in place if it fits, else append with capacity doubling: DAGColorPool::SetLeaf,
+// DAGColorPool.hpp:173-204 with keep_history = false), header words; thread per leaf
+__global__ void k_leaf_alloc(CItems leaf, uint32_t first_leaf, uint32_t n_leaves, uint32_t sbits, const uint32_t *__restrict__ flag,
+                             const uint32_t *__restrict__ fscan, const uint32_t *__restrict__ bits, const uint32_t *__restrict__ bscan,
+                             uint32_t *cleaves, uint32_t *ctr, uint64_t leaf_cap, uint32_t *chunk_idx) {
+	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+	if (li >= n_leaves)
+		return;
+	const uint64_t S = 1ull << sbits, a = uint64_t(li) << sbits, last = a + S - 1;
+	const uint32_t block_cnt = fscan[last] + flag[last] - fscan[a];
+	const uint32_t total_bits = bscan[last] + bits[last] - bscan[a];
+	const uint32_t macro_cnt = uint32_t((S + (1u << kMacroBits) - 1u) >> kMacroBits);
+	const uint32_t weight_words = (total_bits + 31u) >> 5;
+	const uint32_t data = macro_cnt * 2u + block_cnt * 2u + weight_words + 4u;
+	uint32_t append = (data & 1u) ? data + 1u : data;
+	const uint32_t item = first_leaf + li, old = leaf.oct[item];
+	uint32_t idx = 0xFFFFFFFFu;
+	if (ctag(old) == kTagLeaf) {
+		const uint32_t oi = cdata(old), block = cleaves[oi];
+		if (data <= block)
+			idx = oi; // rewrite in place
+		else
+			append = max(block << 1, append);
+	}
+	uint32_t res;
+	if (idx == 0xFFFFFFFFu) {
+		idx = atomicAdd(&ctr[1], append);
+		if (uint64_t(idx) + append > leaf_cap || uint64_t(idx) + append >= (1ull << 30)) {
+			ctr[2] = 1;
+			chunk_idx[li] = 0xFFFFFFFFu;
+			leaf.result[item] = old; // out of space: keep the old pointer (DAGColorPool.hpp:196-198)
+			return;
+		}
+		cleaves[idx] = append;
+	}
+	res = (kTagLeaf << 30) | idx;
+	cleaves[idx + 1] = macro_cnt, cleaves[idx + 2] = block_cnt, cleaves[idx + 3] = weight_words;
+	chunk_idx[li] = idx;
+	leaf.result[item] = res;
+}
+
+__global__ void __launch_bounds__(kCB) k_zero_weights(uint32_t n_leaves, const uint32_t *__restrict__ chunk_idx, uint32_t *cleaves) {
+	for (uint32_t li = blockIdx.x; li < n_leaves; li += gridDim.x) {
+		const uint32_t idx = chunk_idx[li];
+		if (idx == 0xFFFFFFFFu)
+			continue;
+		const uint32_t off = idx + 4u + cleaves[idx + 1] * 2u + cleaves[idx + 2] * 2u, n = cleaves[idx + 3];
+		for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+			cleaves[off + i] = 0u;
+	}
+}
+
+// macro blocks, block headers and weight bits of every chunk (VBRMacroBlock / VBRBlockHeader, VBRColor.hpp:230-250)
+__global__ void __launch_bounds__(kCB) k_emit(uint64_t n, uint32_t sbits, const uint32_t *__restrict__ colors,
+                                              const uint8_t *__restrict__ bw, const uint32_t *__restrict__ flag,
+                                              const uint32_t *__restrict__ fscan, const uint32_t *__restrict__ bscan,
+                                              const uint32_t *__restrict__ chunk_idx, uint32_t *cleaves) {
+	const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (t >= n)
+		return;
+	const uint32_t li = uint32_t(t >> sbits), idx = chunk_idx[li];
+	if (idx == 0xFFFFFFFFu)
+		return;
+	const uint64_t a = uint64_t(li) << sbits;
+	const uint32_t m = uint32_t(t - a);
+	const uint32_t macro_cnt = cleaves[idx + 1], block_cnt = cleaves[idx + 2];
+	const uint32_t macro_off = idx + 4u, block_off = macro_off + macro_cnt * 2u, weight_off = block_off + block_cnt * 2u;
+	const uint32_t blk = fscan[t] - fscan[a], bit = bscan[t] - bscan[a]; // block index / weight bit index inside the chunk
+	const uint64_t macro_first = a + (uint64_t(m >> kMacroBits) << kMacroBits);
+	const uint32_t macro_bit = bscan[macro_first] - bscan[a];
+	if ((m & ((1u << kMacroBits) - 1u)) == 0u) {
+		cleaves[macro_off + ((m >> kMacroBits) << 1)] = blk;      // first_block
+		cleaves[macro_off + ((m >> kMacroBits) << 1) + 1] = bit; // weight_start
+	}
+	const uint32_t b = bw[t] & 3u;
+	if (flag[t]) {
+		cleaves[block_off + (blk << 1)] = colors[t];
+		cleaves[block_off + (blk << 1) + 1] = ((m & ((1u << kMacroBits) - 1u)) << 18) | (b << 16) | (bit - macro_bit);
+	}
+	if (b) { // VBRBitsetWriter::Push(weight, bits): LSB first, may straddle two words
+		const uint32_t w = uint32_t(bw[t]) >> 2, o = bit & 31u;
+		atomicOr(&cleaves[weight_off + (bit >> 5)], w << o);
+		if (o + b > 32u)
+			atomicOr(&cleaves[weight_off + (bit >> 5) + 1], w >> (32u - o));
+	}
+}
+
+__global__ void k_leaf_report(CItems leaf, uint32_t *parent_child, uint32_t *root_out) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= leaf.n)
+		return;
+	const uint32_t par = leaf.parent[i];
+	if (par == 0xFFFFFFFFu)
+		*root_out = leaf.result[i];
+	else
+		parent_child[par] = leaf.result[i];
+}
+
+template <typename T> static cudaError_t cmalloc(T **p, uint64_t count, cudaStream_t s) {
+	return cudaMallocAsync(reinterpret_cast<void **>(p), std::max<uint64_t>(count, 1) * sizeof(T), s);
+}
+static inline uint32_t cblocks(uint64_t threads) { return uint32_t((threads + kCB - 1) / kCB); }
+
+struct CLevel {
+	CItems v{};
+	cudaStream_t s = nullptr;
+	cudaError_t init(uint32_t cap, bool inner, cudaStream_t stream) {
+		s = stream, v.cap = cap, v.n = 0;
+		cudaError_t e;
+		if ((e = cmalloc(&v.geom, cap, s)) || (e = cmalloc(&v.oct, cap, s)) || (e = cmalloc(&v.pos, cap, s)) ||
+		    (e = cmalloc(&v.parent, cap, s)) || (e = cmalloc(&v.result, cap, s)))
+			return e;
+		if (inner && (e = cmalloc(&v.child, uint64_t(cap) * 8, s)))
+			return e;
+		return cudaSuccess;
+	}
+	void release() {
+		void *ptrs[] = {v.geom, v.oct, v.pos, v.parent, v.result, v.child};
+		for (void *q : ptrs)
+			if (q)
+				cudaFreeAsync(q, s);
+		v = CItems{};
+	}
+};
+
+static hd_status ensure_color_storage(hd_pool *p, uint64_t node_words, uint64_t leaf_words) {
+	cudaStream_t s = p->stream;
+	if (!p->color_ctr) {
+		HD_CUDA_TRY(cudaMalloc(&p->color_ctr, 4 * sizeof(uint32_t)));
+		HD_CUDA_TRY(cudaMemset(p->color_ctr, 0, 4 * sizeof(uint32_t)));
+	}
+	auto grow = [&](uint32_t *&buf, uint64_t &cap, uint64_t used, uint64_t need) -> hd_status {
+		if (need + 8 <= cap)
+			return HD_OK;
+		const uint64_t ncap = std::max<uint64_t>(need * 2 + (1u << 16), cap * 2);
+		uint32_t *nb = nullptr;
+		HD_CUDA_TRY(cudaMalloc(&nb, ncap * 4));
+		HD_CUDA_TRY(cudaMemsetAsync(nb, 0, ncap * 4, s));
+		if (buf && used)
+			HD_CUDA_TRY(cudaMemcpyAsync(nb, buf, used * 4, cudaMemcpyDeviceToDevice, s));
+		HD_CUDA_TRY(cudaStreamSynchronize(s));
+		cudaFree(buf);
+		buf = nb, cap = ncap;
+		return HD_OK;
+	};
+	hd_status st = grow(p->color_nodes, p->color_node_cap, p->color_node_words, node_words);
+	if (st != HD_OK)
+		return st;
+	return grow(p->color_leaves, p->color_leaf_cap, p->color_leaf_words, leaf_words);
+}
+
+} // namespace hd
+
+using namespace hd;
+
+extern "C" {
+
+hd_status hd_color_upload(hd_pool *p, const uint32_t *nodes, uint64_t node_words, const uint32_t *leaves, uint64_t leaf_words) {
+	if (!p || (!nodes && node_words) || (!leaves && leaf_words) || node_words % 8)
+		return HD_ERR_INVALID;
+	HD_CUDA_TRY(cudaSetDevice(p->device));
+	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	p->color_node_words = p->color_leaf_words = 0;
+	hd_status st = ensure_color_storage(p, node_words, leaf_words);
+	if (st != HD_OK)
+		return st;
+	if (node_words)
+		HD_CUDA_TRY(cudaMemcpy(p->color_nodes, nodes, node_words * 4, cudaMemcpyHostToDevice));
+	if (leaf_words)
+		HD_CUDA_TRY(cudaMemcpy(p->color_leaves, leaves, leaf_words * 4, cudaMemcpyHostToDevice));
+	p->color_node_words = node_words, p->color_leaf_words = leaf_words;
+	const uint32_t ctr[4] = {uint32_t(node_words / 8), uint32_t(leaf_words), 0u, 0u};
+	HD_CUDA_TRY(cudaMemcpy(p->color_ctr, ctr, sizeof(ctr), cudaMemcpyHostToDevice));
+	return HD_OK;
+}
+
+hd_status hd_color_config(hd_pool *p, uint32_t leaf_level, uint32_t color_root) {
+	if (!p || leaf_level + 2 > p->geo.node_levels)
+		return HD_ERR_INVALID; // the colour leaf level must lie above the geometry leaf nodes
+	p->color_leaf_level = leaf_level, p->color_root = color_root;
+	return HD_OK;
+}
+uint32_t hd_color_root(const hd_pool *p) { return p ? p->color_root : HD_COLOR_NULL; }
+uint32_t hd_color_leaf_level(const hd_pool *p) { return p ? p->color_leaf_level : 0; }
+
+hd_status hd_color_sizes(hd_pool *p, uint64_t *node_words, uint64_t *leaf_words) {
+	if (!p || !node_words || !leaf_words)
+		return HD_ERR_INVALID;
+	*node_words = p->color_node_words, *leaf_words = p->color_leaf_words;
+	return HD_OK;
+}
+hd_status hd_color_read(hd_pool *p, uint32_t *nodes, uint64_t node_words, uint32_t *leaves, uint64_t leaf_words) {
+	if (!p || node_words > p->color_node_words || leaf_words > p->color_leaf_words)
+		return HD_ERR_INVALID;
+	HD_CUDA_TRY(cudaSetDevice(p->device));
+	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	if (node_words)
+		HD_CUDA_TRY(cudaMemcpy(nodes, p->color_nodes, node_words * 4, cudaMemcpyDeviceToHost));
+	if (leaf_words)
+		HD_CUDA_TRY(cudaMemcpy(leaves, p->color_leaves, leaf_words * 4, cudaMemcpyDeviceToHost));
+	return HD_OK;
+}
+
+hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, uint32_t rgb8, uint32_t paint, uint32_t *root_out,
+                        uint32_t *color_root_out, hd_edit_stats *stats) {
+	if (!p || !edit || !root_out || !color_root_out)
+		return HD_ERR_INVALID;
+	*root_out = root_in, *color_root_out = p->color_root;
+	const bool sphere = edit->kind == HD_EDIT_SPHERE_FILL, aabb = edit->kind == HD_EDIT_AABB_FILL;
+	if (!(sphere || aabb) || (paint && !sphere) || p->color_leaf_level == 0 || p->color_leaf_level + 2 > p->geo.node_levels) {
+		set_error("hd_edit_color: AABB fill, sphere fill or sphere paint with a configured colour pool (hd_color_config)");
+		return HD_ERR_INVALID;
+	}
+	HD_CUDA_TRY(cudaSetDevice(p->device));
+	cudaStream_t s = p->stream;
+	const Geometry &g = p->geo;
+	ColorEdit e{};
+	e.d = *edit, e.rgb8 = rgb8 & 0xFFFFFFu, e.paint = paint ? 1u : 0u;
+	e.voxel_level = g.voxel_level(), e.node_levels = g.node_levels, e.leaf_level = p->color_leaf_level;
+	const uint32_t LL = e.leaf_level, sbits = 3u * (e.voxel_level - LL);
+	if (sbits > 30u) {
+		set_error("colour leaf too large (%u voxel bits)", sbits);
+		return HD_ERR_INVALID;
+	}
+	hd_status st = ensure_color_storage(p, p->color_node_words, p->color_leaf_words);
+	if (st != HD_OK)
+		return st;
+
+	// ---- colour pass over the OLD geometry (node memory is immutable, so the order w.r.t. the geometry edit is free) ----
+	std::vector<CLevel> inner(LL + 1);
+	CLevel leaf;
+	uint32_t *counts = nullptr, *root_dev = nullptr; // counts: [inner created, leaves created, -, overflow]
+	HD_CUDA_TRY(cmalloc(&counts, 4, s));
+	HD_CUDA_TRY(cmalloc(&root_dev, 1, s));
+	auto cleanup = [&]() {
+		for (auto &l : inner)
+			l.release();
+		leaf.release();
+		cudaFreeAsync(counts, s), cudaFreeAsync(root_dev, s);
+		cudaStreamSynchronize(s);
+	};
+	uint32_t hc[4] = {0, 0, 0, 0};
+	auto read_counts = [&]() -> hd_status {
+		HD_CUDA_TRY(cudaMemcpyAsync(hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, s));
+		HD_CUDA_TRY(cudaStreamSynchronize(s));
+		return HD_OK;
+	};
+	// leaf items can be created from any octree level's expansion: size the leaf list for the worst case lazily
+	// (grown by re-running is avoided: capacity = 8 x the widest inner level, which bounds the leaves of one level;
+	// leaves only appear at level LL, i.e. from the expansion of level LL-1, or the root when LL == 0)
+	HD_CUDA_TRY(inner[0].init(1, true, s));
+	HD_CUDA_TRY(leaf.init(1, false, s));
+	HD_CUDA_TRY(cudaMemsetAsync(counts, 0, 16, s));
+	const uint32_t col_root_in = p->color_root;
+	HD_CUDA_TRY(cudaMemcpyAsync(root_dev, &col_root_in, 4, cudaMemcpyHostToDevice, s));
+	k_croot<<<1, 32, 0, s>>>(e, root_in, col_root_in, inner[0].v, leaf.v, counts, root_dev);
+	HD_LAUNCH_CHECK();
+	st = read_counts();
+	if (st != HD_OK) {
+		cleanup();
+		return st;
+	}
+	inner[0].v.n = hc[0], leaf.v.n = hc[1];
+	uint32_t deepest = 0;
+	for (uint32_t l = 0; l < LL && inner[l].v.n; ++l) {
+		const uint64_t cap = uint64_t(inner[l].v.n) * 8;
+		if (cap > 0x7FFFFFF0ull) {
+			cleanup();
+			return HD_ERR_OVERFLOW;
+		}
+		HD_CUDA_TRY(inner[l + 1].init(uint32_t(cap), true, s));
+		if (l + 1 == LL) {
+			leaf.release();
+			HD_CUDA_TRY(leaf.init(uint32_t(cap), false, s));
+		}
+		HD_CUDA_TRY(cudaMemsetAsync(counts, 0, 8, s));
+		k_cdown<<<cblocks(cap), kCB, 0, s>>>(e, l, p->words, p->color_nodes, inner[l].v, inner[l + 1].v, leaf.v, counts);
+		HD_LAUNCH_CHECK();
+		st = read_counts();
+		if (st != HD_OK || hc[3]) {
+			cleanup();
+			return st != HD_OK ? st : HD_ERR_OVERFLOW;
+		}
+		inner[l + 1].v.n = hc[0];
+		if (l + 1 == LL)
+			leaf.v.n = hc[1];
+		deepest = l + 1;
+	}
+
+	// ---- leaves: per-voxel colours -> canonical VBR chunks, in batches of <= 2^26 voxels ----
+	const uint32_t n_leaf = leaf.v.n;
+	uint64_t leaf_voxels = 0;
+	if (n_leaf) {
+		const uint32_t per_batch = std::max<uint32_t>(1u, uint32_t((1ull << 26) >> sbits));
+		for (uint32_t first = 0; first < n_leaf; first += per_batch) {
+			const uint32_t nl = std::min(per_batch, n_leaf - first);
+			const uint64_t n = uint64_t(nl) << sbits;
+			leaf_voxels += n;
+			uint32_t *colors = nullptr, *flag = nullptr, *bits = nullptr, *fscan = nullptr, *bscan = nullptr, *chunk_idx = nullptr;
+			uint8_t *bw = nullptr;
+			HD_CUDA_TRY(cmalloc(&colors, n, s));
+			HD_CUDA_TRY(cmalloc(&bw, n, s));
+			HD_CUDA_TRY(cmalloc(&flag, n, s));
+			HD_CUDA_TRY(cmalloc(&bits, n, s));
+			HD_CUDA_TRY(cmalloc(&fscan, n, s));
+			HD_CUDA_TRY(cmalloc(&bscan, n, s));
+			HD_CUDA_TRY(cmalloc(&chunk_idx, nl, s));
+			k_voxels<<<cblocks(n), kCB, 0, s>>>(e, p->words, p->color_leaves, leaf.v, first, nl, sbits, colors, bw);
+			HD_LAUNCH_CHECK();
+			k_flags<<<cblocks(n), kCB, 0, s>>>(colors, bw, n, sbits, flag, bits);
+			HD_LAUNCH_CHECK();
+			st = exclusive_scan(p, flag, fscan, n);
+			if (st == HD_OK)
+				st = exclusive_scan(p, bits, bscan, n);
+			if (st == HD_OK) { // how many words will this batch append?  grow the leaf array once, before allocating
+				unsigned long long *total = nullptr, need = 0;
+				HD_CUDA_TRY(cmalloc(&total, 1, s));
+				HD_CUDA_TRY(cudaMemsetAsync(total, 0, 8, s));
+				k_leaf_size<<<cblocks(nl), kCB, 0, s>>>(leaf.v, first, nl, sbits, flag, fscan, bits, bscan, p->color_leaves, total);
+				HD_LAUNCH_CHECK();
+				HD_CUDA_TRY(cudaMemcpyAsync(&need, total, 8, cudaMemcpyDeviceToHost, s));
+				HD_CUDA_TRY(cudaStreamSynchronize(s));
+				cudaFreeAsync(total, s);
+				st = ensure_color_storage(p, p->color_node_words, p->color_leaf_words + need);
+			}
+			if (st == HD_OK) {
+				k_leaf_alloc<<<cblocks(nl), kCB, 0, s>>>(leaf.v, first, nl, sbits, flag, fscan, bits, bscan, p->color_leaves, p->color_ctr,
+				                                        p->color_leaf_cap, chunk_idx);
+				HD_LAUNCH_CHECK();
+				k_zero_weights<<<std::min<uint32_t>(nl, 1184u), kCB, 0, s>>>(nl, chunk_idx, p->color_leaves);
+				HD_LAUNCH_CHECK();
+				k_emit<<<cblocks(n), kCB, 0, s>>>(n, sbits, colors, bw, flag, fscan, bscan, chunk_idx, p->color_leaves);
+				HD_LAUNCH_CHECK();
+				uint32_t ctr[4];
+				HD_CUDA_TRY(cudaMemcpyAsync(ctr, p->color_ctr, sizeof(ctr), cudaMemcpyDeviceToHost, s));
+				HD_CUDA_TRY(cudaStreamSynchronize(s));
+				p->color_leaf_words = ctr[1];
+			}
+			cudaFreeAsync(colors, s), cudaFreeAsync(bw, s), cudaFreeAsync(flag, s), cudaFreeAsync(bits, s);
+			cudaFreeAsync(fscan, s), cudaFreeAsync(bscan, s), cudaFreeAsync(chunk_idx, s);
+			if (st != HD_OK) {
+				cleanup();
+				return st;
+			}
+		}
+		k_leaf_report<<<cblocks(n_leaf), kCB, 0, s>>>(leaf.v, LL ? inner[LL - 1].v.child : nullptr, root_dev);
+		HD_LAUNCH_CHECK();
+	}
+
+	// ---- octree nodes bottom-up (SetNode) ----
+	{
+		uint64_t new_nodes = 0;
+		for (uint32_t l = 0; l <= deepest && l < LL; ++l)
+			new_nodes += inner[l].v.n;
+		st = ensure_color_storage(p, p->color_node_words + new_nodes * 8, p->color_leaf_words);
+		if (st != HD_OK) {
+			cleanup();
+			return st;
+		}
+	}
+	for (uint32_t l = std::min(deepest, LL ? LL - 1 : 0) + 1; l-- > 0;) {
+		if (l >= LL || inner[l].v.n == 0)
+			continue;
+		k_cup<<<cblocks(inner[l].v.n), kCB, 0, s>>>(inner[l].v, p->color_nodes, p->color_ctr, p->color_node_cap,
+		                                          l ? inner[l - 1].v.child : nullptr, root_dev);
+		HD_LAUNCH_CHECK();
+	}
+	uint32_t ctr[4], new_color_root;
+	HD_CUDA_TRY(cudaMemcpyAsync(ctr, p->color_ctr, sizeof(ctr), cudaMemcpyDeviceToHost, s));
+	HD_CUDA_TRY(cudaMemcpyAsync(&new_color_root, root_dev, 4, cudaMemcpyDeviceToHost, s));
+	HD_CUDA_TRY(cudaStreamSynchronize(s));
+	cleanup();
+	p->color_node_words = uint64_t(ctr[0]) * 8, p->color_leaf_words = ctr[1];
+	if (ctr[2]) {
+		set_error("colour pool out of space");
+		return HD_ERR_OOM;
+	}
+	p->color_root = new_color_root;
+	*color_root_out = new_color_root;
+
+	// ---- geometry (SphereEditor<kPaint> leaves the voxels alone, main.cpp:133-136) ----
+	if (!paint) {
+		st = hd_edit_batch(p, root_in, edit, 1, root_out, stats);
+		if (st != HD_OK)
+			return st;
+	} else if (stats)
+		memset(stats, 0, sizeof(*stats));
+	if (stats)
+		stats->in_range_voxels = leaf_voxels; // colour voxels re-encoded (diagnostic)
+	return HD_OK;
+}
+
+} // extern "C"

@@ -73,7 +73,10 @@ struct hd_pool {
 	uint32_t *bucket_synced = nullptr; // bucket_words at the last hd_dirty_reset (device)
 
 	uint32_t *color_nodes = nullptr, *color_leaves = nullptr; // DAGColorPool buffers (device)
-	uint64_t color_node_words = 0, color_leaf_words = 0;
+	uint64_t color_node_words = 0, color_leaf_words = 0; // used words (host copy, refreshed after colour edits)
+	uint64_t color_node_cap = 0, color_leaf_cap = 0;     // allocated words
+	uint32_t color_root = HD_COLOR_NULL, color_leaf_level = 0;
+	uint32_t *color_ctr = nullptr; // device: [0] = nodes used, [1] = leaf words used, [2] = out-of-space flag
 
 	uint32_t root = HD_NULL_NODE;
 	bool needs_full_resync = false; // set by hd_gc: replicas must clear before applying the next sync

@@ -161,6 +161,7 @@ void hd_pool_destroy(hd_pool *p) {
 	cudaFree(p->bucket_synced);
 	cudaFree(p->color_nodes);
 	cudaFree(p->color_leaves);
+	cudaFree(p->color_ctr);
 	cudaFree(p->stage_rgba);
 	cudaFree(p->stage_iters);
 	cudaFree(p->stage_fetches);
@@ -253,28 +254,6 @@ hd_status hd_pool_filled_nodes(hd_pool *p, uint32_t *out) {
 		return s;
 	for (uint32_t l = 0; l < p->geo.node_levels; ++l)
 		out[l] = p->filled[l];
-	return HD_OK;
-}
-
-hd_status hd_color_upload(hd_pool *p, const uint32_t *nodes, uint64_t node_words, const uint32_t *leaves,
-                          uint64_t leaf_words) {
-	if (!p || (!nodes && node_words) || (!leaves && leaf_words))
-		return HD_ERR_INVALID;
-	HD_CUDA_TRY(cudaSetDevice(p->device));
-	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
-	cudaFree(p->color_nodes);
-	cudaFree(p->color_leaves);
-	p->color_nodes = p->color_leaves = nullptr;
-	p->color_node_words = node_words, p->color_leaf_words = leaf_words;
-	// +2 words of slack: the decoder may read one weight word past a chunk (trace.frag:295)
-	HD_CUDA_TRY(cudaMalloc(&p->color_nodes, (node_words + 8) * 4));
-	HD_CUDA_TRY(cudaMalloc(&p->color_leaves, (leaf_words + 8) * 4));
-	HD_CUDA_TRY(cudaMemset(p->color_nodes, 0, (node_words + 8) * 4));
-	HD_CUDA_TRY(cudaMemset(p->color_leaves, 0, (leaf_words + 8) * 4));
-	if (node_words)
-		HD_CUDA_TRY(cudaMemcpy(p->color_nodes, nodes, node_words * 4, cudaMemcpyHostToDevice));
-	if (leaf_words)
-		HD_CUDA_TRY(cudaMemcpy(p->color_leaves, leaves, leaf_words * 4, cudaMemcpyHostToDevice));
 	return HD_OK;
 }
 
