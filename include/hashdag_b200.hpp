@@ -249,6 +249,21 @@ public:
 		return roots;
 	}
 
+	// Colour-aware edits: vbr_edit(...) of src/main.cpp:224-230 for AABBEditor / SphereEditor<kFill> with a colour, and
+	// SphereEditor<kPaint> (paint = true).  ConfigureColor = DAGColorPool::Config::leaf_level + SetRoot.  Returns the new
+	// node root; GetColorRoot() is the new colour root (EditResult of main.cpp:161-164).
+	bool ConfigureColor(uint32_t leaf_level, uint32_t color_root = HD_COLOR_NULL) {
+		return (m_last_status = hd_color_config(m_pool, leaf_level, color_root)) == HD_OK;
+	}
+	uint32_t GetColorRoot() const { return hd_color_root(m_pool); }
+	template <typename Editor_T>
+	NodePointer<uint32_t> EditColor(NodePointer<uint32_t> root, const Editor_T &editor, uint32_t rgb8, bool paint = false) {
+		hd_edit_desc d = editor.Desc();
+		uint32_t out = *root, color_root = HD_COLOR_NULL;
+		m_last_status = hd_edit_color(m_pool, *root, &d, rgb8, paint ? 1u : 0u, &out, &color_root, &m_last_stats);
+		return m_last_status == HD_OK ? NodePointer<uint32_t>{out} : root;
+	}
+
 	// pool file (no reference counterpart)
 	bool Save(const char *path) { return (m_last_status = hd_pool_save(m_pool, path)) == HD_OK; }
 	static std::unique_ptr<DAGNodePool> Load(const char *path, int device = 0) {

@@ -306,6 +306,8 @@ class Ref(_Lib):
         L.ref_color_leaf_words.argtypes = [vp]
         L.ref_edit_color.restype = u32
         L.ref_edit_color.argtypes = [vp, vp, u32, C.POINTER(HdEditDesc), u32, C.c_int]
+        L.ref_edit_color_mt.restype = u32
+        L.ref_edit_color_mt.argtypes = [vp, vp, u32, C.POINTER(HdEditDesc), u32, C.c_int, u32]
         L.ref_color_at.restype = C.c_int
         L.ref_color_at.argtypes = [vp, u32, u32, u32, u32, pf]
 
@@ -391,8 +393,9 @@ class RefPool(_PoolBase):
                                         pos.ctypes.data_as(C.POINTER(C.c_float)) if want_pos else None)
         return {"hit": hit, "pos": pos, "n_hits": n}
 
-    def edit_color(self, cpool, root, desc, rgb8, paint=False):
-        return self.L.ref_edit_color(self.h, cpool.h, root, C.byref(desc), rgb8, int(paint))
+    def edit_color(self, cpool, root, desc, rgb8, paint=False, threads=0):
+        """vbr_edit: serial Edit (threads=0) or ThreadedEdit(busy_pool(threads), max_task_level = colour leaf level)."""
+        return self.L.ref_edit_color_mt(self.h, cpool.h, root, C.byref(desc), rgb8, int(paint), threads)
 
 
 class RefColorPool:

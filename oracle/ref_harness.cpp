@@ -521,7 +521,14 @@ uint64_t ref_color_leaf_words(ref_color_pool *c) { return c->pool->leaf_words.lo
 
 // Coloured edit through VBREditorWrapper (VBREditor.hpp:26-107), serial Edit.  paint != 0 selects
 // SphereEditor<kPaint>.  Updates the colour root (main.cpp:239-243) and returns the new node root.
+uint32_t ref_edit_color_mt(ref_pool *p, ref_color_pool *c, uint32_t root, const hd_edit_desc *d, uint32_t rgb8, int paint,
+                           uint32_t threads);
 uint32_t ref_edit_color(ref_pool *p, ref_color_pool *c, uint32_t root, const hd_edit_desc *d, uint32_t rgb8, int paint) {
+	return ref_edit_color_mt(p, c, root, d, rgb8, paint, 0);
+}
+// threads != 0: ThreadedEdit with max_task_level = the colour leaf level, exactly as src/main.cpp:214-223 calls it
+uint32_t ref_edit_color_mt(ref_pool *p, ref_color_pool *c, uint32_t root, const hd_edit_desc *d, uint32_t rgb8, int paint,
+                           uint32_t threads) {
 	RefPool &pool = *p->pool;
 	RefColorPool &cp = *c->pool;
 	hashdag::VBRColor color{hashdag::RGB8Color{rgb8}};
@@ -529,10 +536,13 @@ uint32_t ref_edit_color(ref_pool *p, ref_color_pool *c, uint32_t root, const hd_
 	auto run = [&](auto ed) -> uint32_t {
 		using Ed = decltype(ed);
 		hashdag::VBREditorWrapper<uint32_t, Ed, RefColorPool> w{.editor = ed, .p_octree = &cp, .octree_root = cp.root};
-		return pool.Edit(NPtr{root}, w, [&](NPtr new_root, auto &&state) -> uint32_t {
+		auto done = [&](NPtr new_root, auto &&state) -> uint32_t {
 			cp.root = state.octree_node;
 			return *new_root;
-		});
+		};
+		if (threads)
+			return pool.ThreadedEdit(get_busy_pool(threads), NPtr{root}, w, cp.GetLeafLevel(), done);
+		return pool.Edit(NPtr{root}, w, done);
 	};
 	if (d->kind == HD_EDIT_AABB_FILL)
 		return run(AABBEd{a, b, color});

@@ -203,6 +203,7 @@ struct FileHeader {
 	uint32_t version;
 	hd_config cfg;
 	uint64_t blob_bytes, color_node_words, color_leaf_words;
+	uint32_t color_root, color_leaf_level; // DAGColorPool root + Config::leaf_level
 };
 
 hd_status hd_pool_save(hd_pool *p, const char *path) {
@@ -248,6 +249,7 @@ hd_status hd_pool_save(hd_pool *p, const char *path) {
 	memcpy(fh.magic, "HDAGB200", 8);
 	fh.version = 1, fh.cfg = p->cfg, fh.blob_bytes = blob;
 	fh.color_node_words = cn.size(), fh.color_leaf_words = cl.size();
+	fh.color_root = p->color_root, fh.color_leaf_level = p->color_leaf_level;
 	FILE *f = fopen(path, "wb");
 	if (!f) {
 		set_error("cannot open %s for writing", path);
@@ -306,6 +308,8 @@ hd_status hd_pool_load(const char *path, int device, hd_pool **out) {
 	cudaFree(stg);
 	if (s == HD_OK && (!cn.empty() || !cl.empty()))
 		s = hd_color_upload(p, cn.data(), cn.size(), cl.data(), cl.size());
+	if (s == HD_OK)
+		p->color_root = fh.color_root, p->color_leaf_level = fh.color_leaf_level;
 	if (s != HD_OK) {
 		hd_pool_destroy(p);
 		return s;
