@@ -39,6 +39,8 @@ def check_equal(oracle, hd, cfg, edits, batches=None, root0=NULL):
     exp = opool.canonical(oroot)
     got, mirror = device_canonical(oracle, dev, cfg, groot)
     assert (oroot == NULL) == (groot == NULL)
+    if got["hash"] != exp["hash"]:  # keep the full evidence: this must never happen
+        print("CANONICAL MISMATCH got", got, "exp", exp, "stats", dev.last_stats, "filled", dev.FilledNodes(), flush=True)
     assert got["hash"] == exp["hash"]
     assert got["by_ptr"] == got["by_content"] == exp["by_ptr"], "duplicate or missing nodes"
     assert got["voxels"] == exp["voxels"]

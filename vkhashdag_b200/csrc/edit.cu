@@ -18,13 +18,17 @@
 //                 (append_node, NodePool.hpp:134-157),
 //       k_resolve losers take their winner's pointer; results flow to the parent's child slots.
 // Phase separation makes the append log safe without locks: a bucket scan can only miss nodes whose content
-// differs from the scanner's (equal contents were merged by k_dedup), and reserved-but-unwritten words are
-// zero or partial and can never equal a candidate.  The final voxel set equals sequential application of the
+// differs from the scanner's (equal contents were merged by k_dedup).  A scan may still observe a node another warp
+// is in the middle of writing: for inner nodes a half-written node can never equal a candidate (unwritten child
+// slots are 0, no child pointer is 0); a leaf word CAN be 0, so leaves are published with a single 64-bit store
+// (found the hard way: (z0, 0) half-written aliased the valid leaf (z0, 0) in ~10 % of cold runs).
+// The final voxel set equals sequential application of the
 // batch, hence the canonical DAG is identical to the reference's; pointer values are not.
 #include "common.cuh"
 #include "editors.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace hd {
@@ -608,8 +612,16 @@ __global__ void __launch_bounds__(kBlock) k_upsert(Geometry g, uint32_t level, b
 					}
 					const uint32_t prev = atomicCAS(bucket_words + bucket, old, at + nw);
 					if (prev == old) {
-						for (uint32_t i = 0; i < nw; ++i)
-							words[base + at + i] = me[i];
+						// Concurrent scanners of this bucket may observe the node half-written.  For inner nodes that
+						// is harmless (an unwritten child slot is 0 and no child pointer is 0), but a leaf word CAN
+						// legitimately be 0: a half-written leaf (z0, 0) would equal the valid leaf (z0, 0) of another
+						// candidate.  Leaves are therefore published with ONE 64-bit store (8-byte aligned, atomic):
+						// a scanner sees (0, 0) — never a stored leaf — or the whole leaf.
+						if (is_leaf)
+							*reinterpret_cast<uint2 *>(words + base + at) = make_uint2(c0, c1);
+						else
+							for (uint32_t i = 0; i < nw; ++i)
+								words[base + at + i] = me[i];
 						found = base + at;
 						++st_nodes;
 						st_words += at + nw - old;
@@ -722,6 +734,7 @@ static hd_status scratch_init(hd_pool *p) {
 	auto *s = new EditScratch();
 	p->edit = s;
 	HD_CUDA_TRY(cudaMalloc(&s->ctr, sizeof(DevCounters)));
+	HD_CUDA_TRY(cudaMemset(s->ctr, 0, sizeof(DevCounters)));
 	HD_CUDA_TRY(cudaMalloc(&s->filled_dev, sizeof(uint32_t) * HD_MAX_NODE_LEVELS));
 	// child pointers of any level >= 1 are >= (buckets at level 0) << bucket_shift
 	s->fast_scan = (uint64_t(1) << (p->geo.bucket_bits[0] + p->geo.bucket_shift())) >= 256ull;
@@ -736,6 +749,25 @@ hd_status edit_scratch_free(hd_pool *p) {
 	delete p->edit;
 	p->edit = nullptr;
 	return HD_OK;
+}
+
+// Debug aid (HD_EDIT_VERIFY=1): after a level's upsert, every candidate's pointer must hold exactly its content.
+__global__ void k_verify(uint32_t n, uint32_t stride, bool is_leaf, const uint32_t *cand, const uint8_t *state,
+                         const uint32_t *winner, const uint32_t *result, const uint32_t *words, uint32_t *errs) {
+	const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+	if (item >= n || state[item] == 0)
+		return;
+	const uint32_t *me = cand + size_t(item) * stride;
+	const uint32_t nw = is_leaf ? 2u : 1u + __popc(me[0] & 0xFFu);
+	const uint32_t ptr = state[item] == 1 ? result[winner[item]] : result[item];
+	bool ok = ptr != kNull;
+	for (uint32_t i = 0; i < nw && ok; ++i)
+		ok = words[ptr + i] == me[i];
+	if (!ok) {
+		const uint32_t k = atomicAdd(&errs[0], 1u);
+		if (k < 4)
+			errs[1 + k * 4] = item, errs[2 + k * 4] = ptr, errs[3 + k * 4] = state[item], errs[4 + k * 4] = me[0];
+	}
 }
 
 // dedup + find-or-insert + resolve over n candidates (state!=0) at `level`.
@@ -757,6 +789,19 @@ static hd_status run_upsert(hd_pool *p, uint32_t level, uint32_t n, uint32_t str
 	                                                               fallback, result, p->words, p->bucket_words, s->ctr);
 	HD_LAUNCH_CHECK();
 	HD_CUDA_TRY(cudaFreeAsync(table, p->stream));
+	static const bool verify = getenv("HD_EDIT_VERIFY") != nullptr;
+	if (verify) { // an overflowed bucket legitimately yields the fallback pointer and is reported here too
+		uint32_t *errs = nullptr, host[17];
+		HD_CUDA_TRY(amalloc(&errs, 17, p->stream));
+		HD_CUDA_TRY(cudaMemsetAsync(errs, 0, sizeof(host), p->stream));
+		k_verify<<<grid_for(n), kBlock, 0, p->stream>>>(n, stride, is_leaf, cand, state, winner, result, p->words, errs);
+		HD_CUDA_TRY(cudaMemcpyAsync(host, errs, sizeof(host), cudaMemcpyDeviceToHost, p->stream));
+		HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+		cudaFreeAsync(errs, p->stream);
+		if (host[0])
+			fprintf(stderr, "[hd verify] level %u: %u of %u candidates do not hold their content; first: item %u ptr %u state %u mask %#x\n",
+			        level, host[0], n, host[1], host[2], host[3], host[4]);
+	}
 	return HD_OK;
 }
 
