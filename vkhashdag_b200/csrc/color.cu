@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(256) k_scan_add(uint32_t *out, const uint32_t 
 			out[i + k] += o;
 }
 
-static hd_status exclusive_scan(hd_pool *p, const uint32_t *in, uint32_t *out, uint64_t n) {
+hd_status exclusive_scan(hd_pool *p, const uint32_t *in, uint32_t *out, uint64_t n) {
 	if (n == 0)
 		return HD_OK;
 	const uint64_t blocks = (n + 1023) / 1024;

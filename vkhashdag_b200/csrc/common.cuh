@@ -108,4 +108,6 @@ hd_status ensure_filled(hd_pool *pool);
 hd_status upsert_batch_dev(hd_pool *pool, uint32_t level, uint32_t n, uint32_t stride, const uint32_t *cand_dev,
                            uint32_t *result_dev);
 hd_status set_filled(hd_pool *pool, const std::vector<uint32_t> &filled);
+// device-wide exclusive prefix sum over u32 (color.cu); in == out is allowed
+hd_status exclusive_scan(hd_pool *pool, const uint32_t *in, uint32_t *out, uint64_t n);
 } // namespace hd

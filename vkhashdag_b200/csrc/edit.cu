@@ -751,6 +751,149 @@ hd_status edit_scratch_free(hd_pool *p) {
 	return HD_OK;
 }
 
+// ---- bucket-grouped find-or-insert (large batches) ------------------------------------------------------------------
+// With tens of candidates per bucket, k_upsert re-reads every bucket once per candidate (34 GB of scans for the cfg3
+// batch).  Here the winners are counting-sorted by bucket and ONE CTA owns a bucket: it stages the used prefix in
+// shared memory once, its warps test all candidates of the bucket against that image, and the misses are appended
+// by the same CTA — no CAS, no other writer, nothing half-written for anybody to see.
+constexpr uint32_t kMiss = 0xFFFFFFFDu;
+constexpr int kGroupThreads = 128;
+constexpr uint32_t kGroupMaxWords = 8192; // bucket images up to 32 KB are staged; larger buckets use k_upsert
+
+__global__ void __launch_bounds__(kBlock) k_bucket_count(Geometry g, uint32_t level, uint32_t n, uint32_t stride,
+                                                         const uint32_t *__restrict__ cand, const uint8_t *__restrict__ state,
+                                                         uint32_t *bkt, uint32_t *count) {
+	const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+	if (item >= n || state[item] != 2)
+		return;
+	const bool is_leaf = level == g.node_levels - 1u;
+	const uint32_t *me = cand + size_t(item) * stride;
+	const uint32_t nw = is_leaf ? 2u : 1u + __popc(me[0] & 0xFFu);
+	const uint32_t h = is_leaf ? hash_leaf(me[0], me[1]) : hash_inner(me, nw);
+	const uint32_t b = h & ((1u << g.bucket_bits[level]) - 1u);
+	bkt[item] = b;
+	atomicAdd(&count[b], 1u);
+}
+__global__ void __launch_bounds__(kBlock) k_bucket_scatter(uint32_t n, const uint8_t *__restrict__ state,
+                                                           const uint32_t *__restrict__ bkt, const uint32_t *__restrict__ offset,
+                                                           uint32_t *fill, uint32_t *order) {
+	const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+	if (item >= n || state[item] != 2)
+		return;
+	const uint32_t b = bkt[item];
+	order[offset[b] + atomicAdd(&fill[b], 1u)] = item;
+}
+
+__global__ void __launch_bounds__(kGroupThreads) k_upsert_grouped(Geometry g, uint32_t level, bool fast_scan, uint32_t stride,
+                                                                  const uint32_t *__restrict__ cand,
+                                                                  const uint32_t *__restrict__ fallback, uint32_t *result,
+                                                                  uint32_t *words, uint32_t *bucket_words,
+                                                                  const uint32_t *__restrict__ offset,
+                                                                  const uint32_t *__restrict__ count,
+                                                                  const uint32_t *__restrict__ order, DevCounters *ctr) {
+	extern __shared__ uint32_t img[]; // the bucket's used prefix
+	const uint32_t b = blockIdx.x, cnt = count[b];
+	if (cnt == 0)
+		return;
+	const uint32_t first = offset[b];
+	const bool is_leaf = level == g.node_levels - 1u;
+	const uint32_t bucket = g.level_base[level] + b, base = bucket << g.bucket_shift();
+	const uint32_t bw = bucket_words[bucket], wpp = g.words_per_page(), wpb = g.words_per_bucket();
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	for (uint32_t i = threadIdx.x; i < bw; i += kGroupThreads)
+		img[i] = words[base + i];
+	__syncthreads();
+
+	// phase A: every candidate of the bucket against the staged image (read-only)
+	for (uint32_t c = warp; c < cnt; c += kGroupThreads / 32) {
+		const uint32_t item = order[first + c];
+		const uint32_t *me = cand + size_t(item) * stride;
+		const uint32_t c0 = me[0], c1 = me[1];
+		const uint32_t nw = is_leaf ? 2u : 1u + __popc(c0 & 0xFFu);
+		uint32_t found = kMiss;
+		if (is_leaf) {
+			for (uint32_t off = 0; off < bw && found == kMiss; off += 64u) {
+				const uint32_t p = off + lane * 2u;
+				const bool hit = p + 2u <= bw && img[p] == c0 && img[p + 1] == c1;
+				const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+				if (m)
+					found = base + off + (__ffs(m) - 1u) * 2u;
+			}
+		} else if (fast_scan) {
+			for (uint32_t off = 0; off < bw && found == kMiss; off += 32u) {
+				const uint32_t p = off + lane;
+				bool hit = p + nw <= bw && img[p] == c0;
+				if (hit)
+					for (uint32_t i = 1; i < nw && hit; ++i)
+						hit = img[p + i] == me[i];
+				const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+				if (m)
+					found = base + off + __ffs(m) - 1u;
+			}
+		} else {
+			if (lane == 0)
+				for (uint32_t page = 0; page < bw && found == kMiss; page += wpp) {
+					const uint32_t end = min(page + wpp, bw);
+					for (uint32_t it = page; nw <= end - it;) {
+						const uint32_t hw = img[it] & 0xFFu;
+						if (hw == 0u)
+							break;
+						const uint32_t sz = 1u + __popc(hw);
+						bool same = sz == nw;
+						for (uint32_t i = 0; i < nw && same; ++i)
+							same = img[it + i] == me[i];
+						if (same) {
+							found = base + it;
+							break;
+						}
+						it += sz;
+					}
+				}
+			found = __shfl_sync(0xFFFFFFFFu, found, 0);
+		}
+		if (lane == 0)
+			result[item] = found;
+	}
+	__syncthreads();
+
+	// phase B: warp 0 appends the misses in list order (append_node, NodePool.hpp:134-157); this CTA is the only writer
+	if (warp != 0)
+		return;
+	uint32_t cur = bw, appended = 0, overflow = 0;
+	for (uint32_t c = 0; c < cnt; ++c) {
+		const uint32_t item = order[first + c];
+		if (result[item] != kMiss)
+			continue;
+		const uint32_t *me = cand + size_t(item) * stride;
+		const uint32_t nw = is_leaf ? 2u : 1u + __popc(me[0] & 0xFFu);
+		const uint32_t off = cur & (wpp - 1u);
+		const uint32_t at = off + nw > wpp ? (cur | (wpp - 1u)) + 1u : cur; // never straddle a page; the tail stays zero
+		if (at + nw > wpb) { // bucket full: keep the old node (NodePool.hpp:137-139,195)
+			if (lane == 0)
+				result[item] = fallback ? fallback[item] : kNull;
+			++overflow;
+			continue;
+		}
+		if (lane < nw)
+			words[base + at + lane] = me[lane];
+		if (lane == 0)
+			result[item] = base + at;
+		cur = at + nw;
+		++appended;
+	}
+	if (lane == 0) {
+		bucket_words[bucket] = cur;
+		atomicAdd(&ctr->stats[2], (unsigned long long)cnt);
+		atomicAdd(&ctr->stats[7], (unsigned long long)bw);
+		if (appended) {
+			atomicAdd(&ctr->stats[3], (unsigned long long)appended);
+			atomicAdd(&ctr->stats[4], (unsigned long long)(cur - bw));
+		}
+		if (overflow)
+			atomicAdd(&ctr->stats[5], (unsigned long long)overflow);
+	}
+}
+
 // Debug aid (HD_EDIT_VERIFY=1): after a level's upsert, every candidate's pointer must hold exactly its content.
 __global__ void k_verify(uint32_t n, uint32_t stride, bool is_leaf, const uint32_t *cand, const uint8_t *state,
                          const uint32_t *winner, const uint32_t *result, const uint32_t *words, uint32_t *errs) {
@@ -785,10 +928,36 @@ static hd_status run_upsert(hd_pool *p, uint32_t level, uint32_t n, uint32_t str
 	HD_CUDA_TRY(cudaMemsetAsync(table, 0, tsize * 4, p->stream));
 	k_dedup<<<grid_for(n), kBlock, 0, p->stream>>>(n, stride, is_leaf, cand, state, winner, table, uint32_t(tsize - 1));
 	HD_LAUNCH_CHECK();
-	k_upsert<<<upsert_grid(p, n), kBlock, 0, p->stream>>>(p->geo, level, s->fast_scan, n, stride, cand, state,
-	                                                               fallback, result, p->words, p->bucket_words, s->ctr);
-	HD_LAUNCH_CHECK();
 	HD_CUDA_TRY(cudaFreeAsync(table, p->stream));
+	// large batches: group the winners by bucket (one staged image and one writer per bucket); small ones and pools
+	// whose buckets do not fit a 32 KB image: one warp per winner with a lock-free append
+	static const int grouped_min = getenv("HD_EDIT_GROUPED_MIN") ? atoi(getenv("HD_EDIT_GROUPED_MIN")) : 16384;
+	const uint32_t nb = 1u << p->geo.bucket_bits[level];
+	if (n >= uint32_t(grouped_min) && p->geo.words_per_bucket() <= kGroupMaxWords) {
+		uint32_t *bkt = nullptr, *count = nullptr, *offset = nullptr, *order = nullptr;
+		HD_CUDA_TRY(amalloc(&bkt, n, p->stream));
+		HD_CUDA_TRY(amalloc(&order, n, p->stream));
+		HD_CUDA_TRY(amalloc(&count, nb, p->stream));
+		HD_CUDA_TRY(amalloc(&offset, nb, p->stream));
+		HD_CUDA_TRY(cudaMemsetAsync(count, 0, size_t(nb) * 4, p->stream));
+		k_bucket_count<<<grid_for(n), kBlock, 0, p->stream>>>(p->geo, level, n, stride, cand, state, bkt, count);
+		HD_LAUNCH_CHECK();
+		hd_status ss = exclusive_scan(p, count, offset, nb);
+		if (ss != HD_OK)
+			return ss;
+		HD_CUDA_TRY(cudaMemsetAsync(count, 0, size_t(nb) * 4, p->stream)); // reused as the per-bucket fill cursor...
+		k_bucket_scatter<<<grid_for(n), kBlock, 0, p->stream>>>(n, state, bkt, offset, count, order);
+		HD_LAUNCH_CHECK();
+		// ...which ends up holding the per-bucket candidate count again
+		k_upsert_grouped<<<nb, kGroupThreads, size_t(p->geo.words_per_bucket()) * 4, p->stream>>>(
+		    p->geo, level, s->fast_scan, stride, cand, fallback, result, p->words, p->bucket_words, offset, count, order, s->ctr);
+		HD_LAUNCH_CHECK();
+		cudaFreeAsync(bkt, p->stream), cudaFreeAsync(order, p->stream), cudaFreeAsync(count, p->stream), cudaFreeAsync(offset, p->stream);
+	} else {
+		k_upsert<<<upsert_grid(p, n), kBlock, 0, p->stream>>>(p->geo, level, s->fast_scan, n, stride, cand, state, fallback, result,
+		                                                       p->words, p->bucket_words, s->ctr);
+		HD_LAUNCH_CHECK();
+	}
 	static const bool verify = getenv("HD_EDIT_VERIFY") != nullptr;
 	if (verify) { // an overflowed bucket legitimately yields the fallback pointer and is reported here too
 		uint32_t *errs = nullptr, host[17];
