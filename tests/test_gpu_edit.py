@@ -182,3 +182,78 @@ def test_bucket_full_and_no_page_straddle(oracle, hd, top_bits):
     again = dev.Upsert(1, nodes, 3)
     assert np.array_equal(again, ptrs)
     dev.close()
+
+
+def test_brush_sequence_low_latency_path(oracle, hd):
+    """The interactive loop (src/main.cpp:214-238): one brush editor per call, fill/dig alternating, on a terrain.
+    Every call is served by the low-latency path (one CUDA graph, device-resident queue counts) and the DAG after the
+    whole sequence is canonically equal to sequential CPU edits."""
+    cfg = abi.default_config(level_count=9, top_level_count=9)
+    vl = cfg.voxel_level
+    res = 1 << vl
+    rng = np.random.default_rng(17)
+    edits = [abi.terrain(vl)]
+    for i in range(24):
+        c = tuple(int(v) for v in rng.integers(res // 4, 3 * res // 4, 3))
+        edits.append(abi.sphere(c, int(rng.integers(3, 40)) ** 2, dig=bool(i & 1)))
+    edits.append(abi.aabb((10, 10, 10), (60, 30, 90)))
+    opool = oracle.pool(cfg)
+    oroot = opool.edit_batch(NULL, edits)
+    dev = hd.DAGNodePool(cfg)
+    groot = dev.EditBatch(NULL, edits[:1])
+    assert dev.last_stats["path"] == "general"          # terrain fills always take the general path
+    for e in edits[1:]:
+        groot = dev.EditBatch(groot, [e])
+        assert dev.last_stats["path"] == "graph" and dev.last_stats["overflow_count"] == 0
+    exp = opool.canonical(oroot)
+    got, _ = device_canonical(oracle, dev, cfg, groot)
+    assert got["hash"] == exp["hash"] and got["by_ptr"] == got["by_content"] == exp["by_ptr"]
+    assert got["voxels"] == exp["voxels"] and got["per_level"] == exp["per_level"]
+    # a small multi-editor batch (<= 32) is one graph launch too, and order inside it is honoured
+    g2 = dev.EditBatch(groot, edits[1:9])
+    assert dev.last_stats["path"] == "graph"
+    o2 = opool.edit_batch(oroot, edits[1:9])
+    assert device_canonical(oracle, dev, cfg, g2)[0]["hash"] == opool.canonical(o2)["hash"]
+    dev.close()
+
+
+_OVERFLOW_SCRIPT = r"""
+import sys
+sys.path.insert(0, {root!r})
+import vkhashdag_b200 as v
+from oracle import bindings
+from vkhashdag_b200 import abi
+O = bindings.Oracle()
+cfg = abi.default_config(level_count=9, top_level_count=9)
+edits = [abi.sphere((256, 256, 256), 150 ** 2), abi.sphere((256, 256, 300), 3 ** 2, dig=True)]
+opool = O.pool(cfg)
+oroot = opool.edit_batch(abi.NULL, edits)
+dev = v.DAGNodePool(cfg)
+r = dev.EditBatch(abi.NULL, edits[:1])
+assert dev.last_stats["path"] == "general", dev.last_stats     # work queues of 64 items cannot hold this sphere
+used = dev.UsedWords()
+r = dev.EditBatch(r, edits[1:])
+assert dev.last_stats["path"] == "graph", dev.last_stats       # the small brush fits
+mirror = O.pool(cfg)
+ranges, bw = dev.Download()
+for off, words in ranges.items():
+    mirror.words_np(off, len(words))[:] = words
+got, exp = O.canonical(mirror.words_ptr, cfg.node_levels, r), opool.canonical(oroot)
+assert got == exp, (got, exp)
+# the aborted low-latency attempt wrote nothing: the pool holds exactly what the reference-order build holds
+assert dev.UsedWords() == int(opool.bucket_words_np().sum()), (dev.UsedWords(), int(opool.bucket_words_np().sum()))
+print("OK")
+"""
+
+
+def test_low_latency_queue_overflow_falls_back(oracle, hd):
+    """With tiny fixed work queues (HD_EDIT_FAST_CAP=64) a big sphere overflows them: the call must be redone by the
+    general path with nothing written in between, and give the same canonical DAG."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HD_EDIT_FAST_CAP="64")
+    out = subprocess.run([sys.executable, "-c", _OVERFLOW_SCRIPT.format(root=root)], env=env, capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr

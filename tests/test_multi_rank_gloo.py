@@ -2,7 +2,8 @@
 
 The pool here is a host-memory stand-in that speaks the same staging format as sync.cu
 ([n_ranges][payload_words][root][0] | {offset,count,payload_offset} x n | payload): the test checks that
-ReplicaSync drives it correctly under a real process group (size broadcast, ONE payload broadcast, root last)."""
+ReplicaSync drives it correctly under a real process group (ONE eager broadcast when the payload fits the eager
+chunk, one more for the remainder when it does not, staging growth on both sides, root last)."""
 import os
 import sys
 
@@ -46,7 +47,8 @@ class HostPool:
     def DirtyPack(self, ptr, capacity):
         r = self._ranges()
         n_words = 4 + 3 * len(r) + sum(c for _, c in r)
-        assert 4 * n_words <= capacity
+        if 4 * n_words > capacity:   # same contract as hd_dirty_pack_dev: report the size, change nothing
+            raise replica.StagingTooSmall(4 * n_words)
         buf = np.ctypeslib.as_array((np.ctypeslib.ctypes.c_uint32 * n_words).from_address(ptr))
         buf[:4] = [len(r), sum(c for _, c in r), self.root, 0]
         poff = 0
@@ -77,9 +79,14 @@ def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     pool = HostPool()
-    sync = replica.ReplicaSync(pool, dist, device="cpu", capacity_bytes=64)  # tiny: forces the grow path
+    # rounds 0-2: tiny staging + tiny eager chunk -> grow path and the two-collective path;
+    # rounds 3-5: roomy eager chunk -> exactly one collective per publish
+    sync = replica.ReplicaSync(pool, dist, device="cpu", capacity_bytes=64)
     rng = np.random.default_rng(42)
-    for round_ in range(3):
+    for round_ in range(6):
+        if round_ == 3:
+            assert sync.collectives == 6   # every tiny round needed the remainder broadcast
+            sync = replica.ReplicaSync(pool, dist, device="cpu", capacity_bytes=1 << 16, eager_bytes=1 << 12)
         if rank == 0:   # the editing rank appends nodes and moves the root
             for _ in range(5):
                 b = int(rng.integers(0, 16))
@@ -88,6 +95,7 @@ def _worker(rank, world, port, q):
                     pool.root = pool.append(b, rng.integers(1, 2 ** 32, n, dtype=np.uint64).astype(np.uint32))
         nbytes = sync.publish(src=0)
         assert nbytes >= 16
+    assert sync.collectives == 3
     # tile partition: each rank owns t % world == rank; together they cover the frame exactly once
     W, H, T = 200, 130, 64
     mine = replica.local_tiles(W, H, T, T, rank, world)
@@ -115,7 +123,7 @@ def test_replica_sync_and_tile_partition_world2():
         assert p.exitcode == 0
     (_, w0, bw0, root0, ap0, part0), (_, w1, bw1, root1, ap1, part1) = res
     assert np.array_equal(w0, w1) and np.array_equal(bw0, bw1) and root0 == root1 != 0xFFFFFFFF
-    assert bw0.sum() > 0 and ap0 == 0 and ap1 == 3          # replica applied once per publish, editor never
+    assert bw0.sum() > 0 and ap0 == 0 and ap1 == 6          # replica applied once per publish, editor never
     W, H, T = 200, 130, 64
     frame = replica.assemble_frame([part0, part1], W, H, T, T, world)
     ys, xs = np.mgrid[0:H, 0:W]

@@ -63,7 +63,7 @@ SYMBOLS = [
     "hd_dirty_apply_dev", "hd_dirty_reset", "hd_pool_used_words", "hd_sync", "hd_kernel_launches", "hd_pool_save",
     "hd_pool_load", "hd_gc", "hd_trace_submit", "hd_trace_collect", "hd_beam_dev",
     "hd_trace_with_beam_dev", "hd_trace_with_beam", "hd_color_config", "hd_color_root", "hd_color_leaf_level",
-    "hd_color_sizes", "hd_color_read", "hd_edit_color",
+    "hd_color_sizes", "hd_color_read", "hd_edit_color", "hd_edit_last_path",
 ]
 
 
@@ -129,6 +129,8 @@ def lib():
     L.hd_traverse_ray.argtypes = [vp, u32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(ci),
                                   C.POINTER(C.c_float)]
     L.hd_dirty_count.argtypes = [vp, pu32, C.POINTER(u64)]
+    L.hd_edit_last_path.argtypes = [vp]
+    L.hd_edit_last_path.restype = u32
     L.hd_dirty_ranges.argtypes = [vp, C.POINTER(HdDirtyRange), u32, pu32]
     L.hd_dirty_pack_dev.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.hd_dirty_apply_dev.argtypes = [vp, vp, u64]
@@ -254,6 +256,7 @@ class DAGNodePool:
         st = HdEditStats()
         _check(self._L.hd_edit_batch(self._h, root, arr, len(arr), C.byref(out), C.byref(st)))
         self.last_stats = st.as_dict()
+        self.last_stats["path"] = "graph" if self._L.hd_edit_last_path(self._h) else "general"
         return out.value
 
     def Upsert(self, level, nodes, words_each):
@@ -445,8 +448,13 @@ class DAGNodePool:
         return [(arr[i].word_offset, arr[i].word_count) for i in range(min(n, got.value))]
 
     def DirtyPack(self, staging_dev_ptr, capacity_bytes):
+        """Pack the dirty ranges into a device staging buffer; raises replica.StagingTooSmall(need) if it cannot hold them."""
         b = C.c_uint64()
-        _check(self._L.hd_dirty_pack_dev(self._h, staging_dev_ptr, capacity_bytes, C.byref(b)))
+        st = self._L.hd_dirty_pack_dev(self._h, staging_dev_ptr, capacity_bytes, C.byref(b))
+        if st == HD_ERR_OVERFLOW and b.value > capacity_bytes:
+            from .replica import StagingTooSmall
+            raise StagingTooSmall(b.value)
+        _check(st)
         return b.value
 
     def DirtyApply(self, staging_dev_ptr, packed_bytes):

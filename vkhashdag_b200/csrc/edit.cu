@@ -43,11 +43,21 @@ struct DevCounters {
 	uint32_t has_long; // some list of the level just expanded is longer than 32 entries -> k_down_long must run
 	uint32_t root_out;
 	uint32_t error; // 1 = scratch overflow
+	// low-latency path (one CUDA graph, no host round trips): item / list-entry counts of every level stay on the device
+	uint32_t lvl_items[HD_MAX_NODE_LEVELS];
+	uint32_t lvl_entries[HD_MAX_NODE_LEVELS];
 };
 
 // One BFS level of work items (device arrays, SoA).
 struct LevelView {
-	uint32_t n;          // items
+	uint32_t n;          // items (host-known); ignored when n_dev is set
+	const uint32_t *n_dev; // device-resident item count (low-latency path) or NULL
+	const uint32_t *err_dev; // with n_dev: DevCounters::error — once a queue overflowed, every later kernel sees 0 items
+	__device__ __forceinline__ uint32_t count() const {
+		if (!n_dev)
+			return n;
+		return *err_dev ? 0u : min(*n_dev, cap);
+	}
 	uint32_t cap;        // item capacity
 	uint32_t cap_entries;
 	uint32_t *cur;       // current node pointer of the item (after Fill/Clear substitution)
@@ -64,10 +74,38 @@ struct LevelView {
 	uint32_t *winner;    // winner item of a loser
 };
 
+// Low-latency path for small batches (the interactive brush of src/main.cpp:214-238 is ONE editor per call): every
+// level's work queue lives in a fixed arena, the item counts stay on the device, and the whole rebuild — root
+// classification, every k_down, the leaf pass, every level's dedup / find-or-insert / resolve — is ONE instantiated
+// CUDA graph.  A call costs one graph launch and one 16-byte-aligned counter read-back instead of ~2 host round trips
+// per level.  A queue that turns out too small sets DevCounters::error before anything touches the pool (k_upsert
+// checks it), and the call falls back to the exactly-sized general path.
+constexpr uint32_t kFastMaxEdits = 32; // lists never exceed 32 entries -> k_down_long is never needed
+struct FastDyn {
+	uint32_t root, n_edits, pad[2];
+	hd_edit_desc edits[kFastMaxEdits];
+};
+struct FastPath {
+	bool tried = false, ok = false;
+	std::vector<LevelView> lv;
+	std::vector<uint32_t *> table;
+	std::vector<uint32_t> table_size;
+	char *arena = nullptr;
+	size_t tables_off = 0, tables_bytes = 0;
+	FastDyn *dyn_host = nullptr, *dyn_dev = nullptr;
+	DevCounters *ctr_host = nullptr;
+	uint32_t *iota_dev = nullptr;
+	cudaGraph_t graph = nullptr;
+	cudaGraphExec_t exec = nullptr;
+	uint32_t kernels = 0;
+};
+
 struct EditScratch {
 	DevCounters *ctr = nullptr;
 	uint32_t *filled_dev = nullptr;
 	bool fast_scan = true;
+	FastPath fast;
+	uint32_t last_path = 0; // hd_edit_last_path
 };
 
 __device__ __forceinline__ uint64_t pack_pos(uint32_t x, uint32_t y, uint32_t z) {
@@ -183,8 +221,9 @@ __device__ inline void write_list(const hd_edit_desc *__restrict__ edits, const 
 
 // Allocate one slot in the next level (and `count` list entries) with warp-aggregated atomics.
 // Must be called by all 32 lanes of the warp (lanes without work pass want = false).
-__device__ __forceinline__ bool alloc_item(DevCounters *ctr, bool want, uint32_t count, uint32_t cap, uint32_t cap_entries,
-                                           uint32_t &item, uint32_t &entry_off) {
+__device__ __forceinline__ bool alloc_item(DevCounters *ctr, uint32_t *items_ctr, uint32_t *entries_ctr, bool want,
+                                           uint32_t count, uint32_t cap, uint32_t cap_entries, uint32_t &item,
+                                           uint32_t &entry_off) {
 	const uint32_t full = 0xFFFFFFFFu;
 	const uint32_t wants = __ballot_sync(full, want);
 	if (!wants)
@@ -200,8 +239,8 @@ __device__ __forceinline__ bool alloc_item(DevCounters *ctr, bool want, uint32_t
 	const uint32_t total_entries = __shfl_sync(full, scan, 31);
 	uint32_t base_item = 0, base_entry = 0;
 	if (lane == 0) {
-		base_item = atomicAdd(&ctr->next_items, __popc(wants));
-		base_entry = atomicAdd(&ctr->next_entries, total_entries);
+		base_item = atomicAdd(items_ctr, __popc(wants));
+		base_entry = atomicAdd(entries_ctr, total_entries);
 	}
 	base_item = __shfl_sync(full, base_item, 0);
 	base_entry = __shfl_sync(full, base_entry, 0);
@@ -265,9 +304,12 @@ __device__ inline uint2 warp_filter_write(const hd_edit_desc *__restrict__ edits
 }
 
 // Root classification (edit_switch on the root, NodePool.hpp:405-413).  One warp.
+// `dyn` (low-latency path): {root, n_edits} live in device memory so that one instantiated graph serves every call.
 __global__ void k_root(Geometry g, const hd_edit_desc *__restrict__ edits, uint32_t n_edits,
                        const uint32_t *__restrict__ iota, const uint32_t *__restrict__ filled, uint32_t root,
-                       LevelView out, DevCounters *ctr) {
+                       LevelView out, DevCounters *ctr, const uint32_t *__restrict__ dyn) {
+	if (dyn)
+		root = dyn[0], n_edits = dyn[1];
 	const uint32_t bits = g.voxel_level();
 	const WarpFiltered f = warp_filter_count(edits, iota, n_edits, bits, 0, 0, 0, root, filled[0]);
 	uint2 r = make_uint2(0u, 0u);
@@ -281,6 +323,8 @@ __global__ void k_root(Geometry g, const hd_edit_desc *__restrict__ edits, uint3
 	}
 	ctr->next_items = 1;
 	ctr->next_entries = r.x + r.y;
+	ctr->lvl_items[0] = 1;
+	ctr->lvl_entries[0] = r.x + r.y;
 	out.cur[0] = f.cur;
 	out.pos[0] = 0;
 	out.parent[0] = 0xFFFFFFFFu;
@@ -295,7 +339,7 @@ __global__ void __launch_bounds__(kBlock) k_down_long(Geometry g, uint32_t level
                                                       DevCounters *ctr) {
 	const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
 	const uint32_t item = w >> 3, c = w & 7u;
-	if (item >= in.n)
+	if (item >= in.n) // host-sized launch only (lists longer than 32 never take the low-latency path)
 		return;
 	const uint32_t len = in.list_len[item];
 	if (len <= 32u)
@@ -348,48 +392,52 @@ __global__ void __launch_bounds__(kBlock) k_down_long(Geometry g, uint32_t level
 		in.child_new[size_t(item) * 8u + c] = result;
 }
 
-// Top-down expansion: thread per (item, child).
+// Top-down expansion: thread per (item, child); whole warps stride over the level (one trip when the host sized the
+// grid from a known item count, a grid-stride loop over the device-resident count on the low-latency path).
 __global__ void __launch_bounds__(kBlock) k_down(Geometry g, uint32_t level /* of `in` */,
                                                  const uint32_t *__restrict__ words,
                                                  const hd_edit_desc *__restrict__ edits,
                                                  const uint32_t *__restrict__ filled, LevelView in, LevelView out,
-                                                 DevCounters *ctr) {
-	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t item = t >> 3, c = t & 7u;
-	const bool valid = item < in.n;
-	Filtered f{kNull, 0u, 0u, 0u};
-	uint32_t x = 0, y = 0, z = 0, len = 0;
-	const uint32_t *list = nullptr;
+                                                 DevCounters *ctr, uint32_t *items_ctr, uint32_t *entries_ctr) {
+	const uint32_t n8 = in.count() * 8u, lane = threadIdx.x & 31u;
 	const uint32_t bits = g.voxel_level() - (level + 1u);
-	if (valid) {
-		const uint32_t cur = in.cur[item];
-		uint32_t child = kNull;
-		if (cur != kNull) { // get_unpacked_node_array, NodePool.hpp:278-309
-			const uint32_t mask = words[cur];
-			if (mask >> c & 1u)
-				child = words[cur + 1u + __popc(mask & ((1u << c) - 1u))];
+	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t - lane < n8; t += gridDim.x * blockDim.x) {
+		const uint32_t item = t >> 3, c = t & 7u;
+		const bool valid = t < n8;
+		Filtered f{kNull, 0u, 0u, 0u};
+		uint32_t x = 0, y = 0, z = 0, len = 0;
+		const uint32_t *list = nullptr;
+		if (valid) {
+			const uint32_t cur = in.cur[item];
+			uint32_t child = kNull;
+			if (cur != kNull) { // get_unpacked_node_array, NodePool.hpp:278-309
+				const uint32_t mask = words[cur];
+				if (mask >> c & 1u)
+					child = words[cur + 1u + __popc(mask & ((1u << c) - 1u))];
+			}
+			unpack_pos(in.pos[item], x, y, z);
+			x = (x << 1) | (c & 1u), y = (y << 1) | ((c >> 1) & 1u), z = (z << 1) | ((c >> 2) & 1u); // NodeCoord.hpp:18-28
+			list = in.lists + in.list_off[item];
+			len = in.list_len[item];
+			if (len <= 32u)
+				f = filter_list(edits, list, len, bits, x, y, z, child, filled[level + 1u]);
 		}
-		unpack_pos(in.pos[item], x, y, z);
-		x = (x << 1) | (c & 1u), y = (y << 1) | ((c >> 1) & 1u), z = (z << 1) | ((c >> 2) & 1u); // NodeCoord.hpp:18-28
-		list = in.lists + in.list_off[item];
-		len = in.list_len[item];
-		if (len <= 32u)
-			f = filter_list(edits, list, len, bits, x, y, z, child, filled[level + 1u]);
-	}
-	uint32_t slot, entry_off;
-	const bool made = alloc_item(ctr, valid && f.count != 0, f.count, out.cap, out.cap_entries, slot, entry_off);
-	if (!valid || len > 32u)
-		return; // long lists: k_down_long
-	if (made) {
-		out.cur[slot] = f.cur;
-		out.pos[slot] = pack_pos(x, y, z);
-		out.parent[slot] = (item << 3) | c;
-		out.list_off[slot] = entry_off;
-		out.list_len[slot] = f.count;
-		write_list(edits, list, len, bits, x, y, z, f, out.lists + entry_off);
-		in.child_new[size_t(item) * 8u + c] = kPending;
-	} else {
-		in.child_new[size_t(item) * 8u + c] = f.cur;
+		uint32_t slot, entry_off;
+		const bool made = alloc_item(ctr, items_ctr, entries_ctr, valid && f.count != 0, f.count, out.cap, out.cap_entries,
+		                             slot, entry_off);
+		if (!valid || len > 32u)
+			continue; // long lists: k_down_long
+		if (made) {
+			out.cur[slot] = f.cur;
+			out.pos[slot] = pack_pos(x, y, z);
+			out.parent[slot] = (item << 3) | c;
+			out.list_off[slot] = entry_off;
+			out.list_len[slot] = f.count;
+			write_list(edits, list, len, bits, x, y, z, f, out.lists + entry_off);
+			in.child_new[size_t(item) * 8u + c] = kPending;
+		} else {
+			in.child_new[size_t(item) * 8u + c] = f.cur;
+		}
 	}
 }
 
@@ -398,9 +446,9 @@ __global__ void __launch_bounds__(kBlock) k_down(Geometry g, uint32_t level /* o
 __global__ void __launch_bounds__(kBlock) k_leaf(Geometry g, const uint32_t *__restrict__ words,
                                                  const hd_edit_desc *__restrict__ edits, LevelView lv,
                                                  DevCounters *ctr) {
-	const uint32_t lane = threadIdx.x & 31u;
-	const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	if (item < lv.n) {
+	const uint32_t lane = threadIdx.x & 31u, n = lv.count();
+	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n; item += warps) {
 		const uint32_t cur = lv.cur[item];
 		const uint32_t *list = lv.lists + lv.list_off[item];
 		const uint32_t len = lv.list_len[item];
@@ -439,10 +487,7 @@ __global__ void __launch_bounds__(kBlock) k_leaf(Geometry g, const uint32_t *__r
 }
 
 // Bottom-up re-pack of inner items (edit_node tail, NodePool.hpp:384-395).  Thread per item.
-__global__ void __launch_bounds__(kBlock) k_assemble(const uint32_t *__restrict__ words, LevelView lv) {
-	const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
-	if (item >= lv.n)
-		return;
+__device__ __forceinline__ void assemble_item(const uint32_t *__restrict__ words, const LevelView &lv, uint32_t item) {
 	const uint32_t cur = lv.cur[item];
 	uint32_t old_mask = 0;
 	if (cur != kNull)
@@ -475,38 +520,47 @@ __global__ void __launch_bounds__(kBlock) k_assemble(const uint32_t *__restrict_
 	lv.state[item] = st;
 	lv.result[item] = res;
 }
+__global__ void __launch_bounds__(kBlock) k_assemble(const uint32_t *__restrict__ words, LevelView lv) {
+	const uint32_t n = lv.count();
+	for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n; item += gridDim.x * blockDim.x)
+		assemble_item(words, lv, item);
+}
 
 // In-batch dedup: one winner per distinct candidate content.  Thread per item.
 __global__ void __launch_bounds__(kBlock) k_dedup(uint32_t n, uint32_t stride, bool is_leaf,
                                                   const uint32_t *__restrict__ cand, uint8_t *state, uint32_t *winner,
-                                                  uint32_t *table, uint32_t table_mask) {
-	const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
-	if (item >= n || state[item] == 0)
-		return;
-	const uint32_t *me = cand + size_t(item) * stride;
-	const uint32_t nw = is_leaf ? 2u : 1u + __popc(me[0] & 0xFFu);
-	uint64_t h = 0x9e3779b97f4a7c15ull;
-	for (uint32_t i = 0; i < nw; ++i)
-		h = mix64(h ^ me[i]) + i;
-	uint32_t slot = uint32_t(h >> 20) & table_mask;
-	for (;;) {
-		uint32_t v = table[slot];
-		if (v == 0u) {
-			v = atomicCAS(&table[slot], 0u, item + 1u);
+                                                  uint32_t *table, uint32_t table_mask, const uint32_t *n_dev,
+                                                  const uint32_t *err_dev) {
+	if (n_dev)
+		n = *err_dev ? 0u : *n_dev;
+	for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n; item += gridDim.x * blockDim.x) {
+		if (state[item] == 0)
+			continue;
+		const uint32_t *me = cand + size_t(item) * stride;
+		const uint32_t nw = is_leaf ? 2u : 1u + __popc(me[0] & 0xFFu);
+		uint64_t h = 0x9e3779b97f4a7c15ull;
+		for (uint32_t i = 0; i < nw; ++i)
+			h = mix64(h ^ me[i]) + i;
+		uint32_t slot = uint32_t(h >> 20) & table_mask;
+		for (;;) {
+			uint32_t v = table[slot];
 			if (v == 0u) {
-				state[item] = 2; // winner
-				return;
+				v = atomicCAS(&table[slot], 0u, item + 1u);
+				if (v == 0u) {
+					state[item] = 2; // winner
+					break;
+				}
 			}
+			const uint32_t *other = cand + size_t(v - 1u) * stride;
+			bool same = true;
+			for (uint32_t i = 0; i < nw && same; ++i)
+				same = other[i] == me[i];
+			if (same) {
+				winner[item] = v - 1u;
+				break;
+			}
+			slot = (slot + 1u) & table_mask;
 		}
-		const uint32_t *other = cand + size_t(v - 1u) * stride;
-		bool same = true;
-		for (uint32_t i = 0; i < nw && same; ++i)
-			same = other[i] == me[i];
-		if (same) {
-			winner[item] = v - 1u;
-			return;
-		}
-		slot = (slot + 1u) & table_mask;
 	}
 }
 
@@ -516,7 +570,12 @@ __global__ void __launch_bounds__(kBlock) k_upsert(Geometry g, uint32_t level, b
                                                    uint32_t stride, const uint32_t *__restrict__ cand,
                                                    const uint8_t *__restrict__ state, const uint32_t *__restrict__ fallback,
                                                    uint32_t *result, uint32_t *words, uint32_t *bucket_words,
-                                                   DevCounters *ctr) {
+                                                   DevCounters *ctr, const uint32_t *n_dev) {
+	if (n_dev) { // low-latency path: the count lives on the device; a scratch overflow upstream must not touch the pool
+		if (*reinterpret_cast<volatile uint32_t *>(&ctr->error))
+			return;
+		n = *n_dev;
+	}
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	const bool is_leaf = level == g.node_levels - 1u;
@@ -650,17 +709,17 @@ __global__ void __launch_bounds__(kBlock) k_upsert(Geometry g, uint32_t level, b
 
 // Losers copy their winner's pointer; every item reports to its parent's child slot (or the root output).
 __global__ void __launch_bounds__(kBlock) k_resolve(LevelView lv, uint32_t *parent_child_new, DevCounters *ctr) {
-	const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
-	if (item >= lv.n)
-		return;
-	uint32_t res = lv.result[item];
-	if (lv.state[item] == 1)
-		res = lv.result[lv.winner[item]];
-	const uint32_t par = lv.parent[item];
-	if (par == 0xFFFFFFFFu)
-		ctr->root_out = res;
-	else
-		parent_child_new[par] = res;
+	const uint32_t n = lv.count();
+	for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n; item += gridDim.x * blockDim.x) {
+		uint32_t res = lv.result[item];
+		if (lv.state[item] == 1)
+			res = lv.result[lv.winner[item]];
+		const uint32_t par = lv.parent[item];
+		if (par == 0xFFFFFFFFu)
+			ctr->root_out = res;
+		else
+			parent_child_new[par] = res;
+	}
 }
 
 __global__ void k_resolve_flat(uint32_t n, const uint8_t *__restrict__ state, const uint32_t *__restrict__ winner,
@@ -746,6 +805,13 @@ hd_status edit_scratch_free(hd_pool *p) {
 		return HD_OK;
 	cudaFree(p->edit->ctr);
 	cudaFree(p->edit->filled_dev);
+	FastPath &f = p->edit->fast;
+	if (f.exec)
+		cudaGraphExecDestroy(f.exec);
+	if (f.graph)
+		cudaGraphDestroy(f.graph);
+	cudaFree(f.arena), cudaFree(f.dyn_dev), cudaFree(f.iota_dev);
+	cudaFreeHost(f.dyn_host), cudaFreeHost(f.ctr_host);
 	delete p->edit;
 	p->edit = nullptr;
 	return HD_OK;
@@ -926,7 +992,7 @@ static hd_status run_upsert(hd_pool *p, uint32_t level, uint32_t n, uint32_t str
 	uint32_t *table = nullptr;
 	HD_CUDA_TRY(amalloc(&table, tsize, p->stream));
 	HD_CUDA_TRY(cudaMemsetAsync(table, 0, tsize * 4, p->stream));
-	k_dedup<<<grid_for(n), kBlock, 0, p->stream>>>(n, stride, is_leaf, cand, state, winner, table, uint32_t(tsize - 1));
+	k_dedup<<<grid_for(n), kBlock, 0, p->stream>>>(n, stride, is_leaf, cand, state, winner, table, uint32_t(tsize - 1), nullptr, nullptr);
 	HD_LAUNCH_CHECK();
 	HD_CUDA_TRY(cudaFreeAsync(table, p->stream));
 	// large batches: group the winners by bucket (one staged image and one writer per bucket); small ones and pools
@@ -955,7 +1021,7 @@ static hd_status run_upsert(hd_pool *p, uint32_t level, uint32_t n, uint32_t str
 		cudaFreeAsync(bkt, p->stream), cudaFreeAsync(order, p->stream), cudaFreeAsync(count, p->stream), cudaFreeAsync(offset, p->stream);
 	} else {
 		k_upsert<<<upsert_grid(p, n), kBlock, 0, p->stream>>>(p->geo, level, s->fast_scan, n, stride, cand, state, fallback, result,
-		                                                       p->words, p->bucket_words, s->ctr);
+		                                                       p->words, p->bucket_words, s->ctr, nullptr);
 		HD_LAUNCH_CHECK();
 	}
 	static const bool verify = getenv("HD_EDIT_VERIFY") != nullptr;
@@ -1068,7 +1134,7 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 
 	levels.resize(L);
 	HD_CUDA_TRY(levels[0].init(1, n_edits, L == 1, st));
-	k_root<<<1, 32, 0, st>>>(g, edits_dev, n_edits, iota, s->filled_dev, root_in, levels[0].v, s->ctr);
+	k_root<<<1, 32, 0, st>>>(g, edits_dev, n_edits, iota, s->filled_dev, root_in, levels[0].v, s->ctr, nullptr);
 	HD_LAUNCH_CHECK();
 	DevCounters host{};
 	hd_status rs = read_counters(p, host);
@@ -1098,7 +1164,7 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 		// reset per-level cursors (stats keep accumulating)
 		HD_CUDA_TRY(cudaMemsetAsync(&s->ctr->next_items, 0, 3 * sizeof(uint32_t), st));
 		k_down<<<grid_for(uint64_t(in.v.n) * 8), kBlock, 0, st>>>(g, l, p->words, edits_dev, s->filled_dev, in.v, out.v,
-		                                                          s->ctr);
+		                                                          s->ctr, &s->ctr->next_items, &s->ctr->next_entries);
 		HD_LAUNCH_CHECK();
 		if (long_lists) {
 			k_down_long<<<grid_for(uint64_t(in.v.n) * 8 * 32), kBlock, 0, st>>>(g, l, p->words, edits_dev, s->filled_dev,
@@ -1165,6 +1231,167 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 	return HD_OK;
 }
 
+// ---- low-latency path ------------------------------------------------------------------------------------------
+static uint32_t fast_grid(hd_pool *p, uint64_t threads) {
+	static int sms = 0;
+	if (!sms)
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+	return uint32_t(std::max<uint64_t>(1, std::min<uint64_t>((threads + kBlock - 1) / kBlock, uint64_t(sms) * 8)));
+}
+
+// Enqueue the whole rebuild on the pool's stream with device-resident counts (captured once into a graph).
+static hd_status fast_enqueue(hd_pool *p) {
+	const Geometry &g = p->geo;
+	EditScratch *s = p->edit;
+	FastPath &f = s->fast;
+	cudaStream_t st = p->stream;
+	const uint32_t L = g.node_levels;
+	HD_CUDA_TRY(cudaMemcpyAsync(f.dyn_dev, f.dyn_host, sizeof(FastDyn), cudaMemcpyHostToDevice, st));
+	HD_CUDA_TRY(cudaMemsetAsync(s->ctr, 0, sizeof(DevCounters), st));
+	HD_CUDA_TRY(cudaMemsetAsync(f.arena + f.tables_off, 0, f.tables_bytes, st));
+	k_root<<<1, 32, 0, st>>>(g, f.dyn_dev->edits, 0, f.iota_dev, s->filled_dev, 0, f.lv[0], s->ctr, &f.dyn_dev->root);
+	HD_LAUNCH_CHECK();
+	for (uint32_t l = 0; l + 1 < L; ++l) {
+		k_down<<<fast_grid(p, uint64_t(f.lv[l].cap) * 8), kBlock, 0, st>>>(g, l, p->words, f.dyn_dev->edits, s->filled_dev, f.lv[l],
+		                                                                 f.lv[l + 1], s->ctr, &s->ctr->lvl_items[l + 1],
+		                                                                 &s->ctr->lvl_entries[l + 1]);
+		HD_LAUNCH_CHECK();
+	}
+	for (uint32_t l = L; l-- > 0;) {
+		const LevelView &v = f.lv[l];
+		const bool leaf = l == L - 1;
+		if (leaf)
+			k_leaf<<<fast_grid(p, uint64_t(v.cap) * 32), kBlock, 0, st>>>(g, p->words, f.dyn_dev->edits, v, s->ctr);
+		else
+			k_assemble<<<fast_grid(p, v.cap), kBlock, 0, st>>>(p->words, v);
+		HD_LAUNCH_CHECK();
+		k_dedup<<<fast_grid(p, v.cap), kBlock, 0, st>>>(0, leaf ? 2 : 9, leaf, v.cand, v.state, v.winner, f.table[l],
+		                                               f.table_size[l] - 1, v.n_dev, v.err_dev);
+		HD_LAUNCH_CHECK();
+		k_upsert<<<fast_grid(p, uint64_t(v.cap) * 32), kBlock, 0, st>>>(g, l, s->fast_scan, 0, leaf ? 2 : 9, v.cand, v.state, v.cur,
+		                                                              v.result, p->words, p->bucket_words, s->ctr, v.n_dev);
+		HD_LAUNCH_CHECK();
+		k_resolve<<<fast_grid(p, v.cap), kBlock, 0, st>>>(v, l ? f.lv[l - 1].child_new : nullptr, s->ctr);
+		HD_LAUNCH_CHECK();
+	}
+	HD_CUDA_TRY(cudaMemcpyAsync(f.ctr_host, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+	return HD_OK;
+}
+
+static hd_status fast_build(hd_pool *p) {
+	const Geometry &g = p->geo;
+	EditScratch *s = p->edit;
+	FastPath &f = s->fast;
+	const uint32_t L = g.node_levels;
+	static const uint32_t cap_max = getenv("HD_EDIT_FAST_CAP") ? uint32_t(atoi(getenv("HD_EDIT_FAST_CAP"))) : (1u << 18);
+	f.lv.assign(L, LevelView{});
+	f.table.assign(L, nullptr), f.table_size.assign(L, 0);
+	// pass 1 sizes the arena, pass 2 hands out the pointers
+	size_t total = 0;
+	for (int pass = 0; pass < 2; ++pass) {
+		size_t off = 0;
+		auto take = [&](size_t bytes) {
+			char *ptr = pass ? f.arena + off : nullptr;
+			off += (bytes + 255) & ~size_t(255);
+			return ptr;
+		};
+		for (uint32_t l = 0; l < L; ++l) {
+			const uint64_t full = l >= 11 ? ~0ull : 1ull << (3 * l); // 8^l nodes exist at level l
+			const uint32_t cap = uint32_t(std::min<uint64_t>(full, cap_max));
+			const uint32_t cap_e = uint32_t(std::min<uint64_t>(uint64_t(cap) * kFastMaxEdits, uint64_t(cap_max) * 4));
+			const bool leaf = l == L - 1;
+			LevelView &v = f.lv[l];
+			v.n = 0, v.cap = cap, v.cap_entries = cap_e;
+			v.n_dev = &s->ctr->lvl_items[l], v.err_dev = &s->ctr->error;
+			v.cur = (uint32_t *)take(size_t(cap) * 4), v.pos = (uint64_t *)take(size_t(cap) * 8);
+			v.list_off = (uint32_t *)take(size_t(cap) * 4), v.list_len = (uint32_t *)take(size_t(cap) * 4);
+			v.parent = (uint32_t *)take(size_t(cap) * 4), v.result = (uint32_t *)take(size_t(cap) * 4);
+			v.winner = (uint32_t *)take(size_t(cap) * 4), v.state = (uint8_t *)take(cap);
+			v.lists = (uint32_t *)take(size_t(cap_e) * 4);
+			v.cand = (uint32_t *)take(size_t(cap) * (leaf ? 2 : 9) * 4);
+			v.child_new = leaf ? nullptr : (uint32_t *)take(size_t(cap) * 8 * 4);
+		}
+		f.tables_off = off;
+		for (uint32_t l = 0; l < L; ++l) { // the dedup tables are contiguous: one memset clears them all
+			uint32_t ts = 64;
+			while (ts < f.lv[l].cap * 2u)
+				ts <<= 1;
+			f.table_size[l] = ts;
+			f.table[l] = (uint32_t *)take(size_t(ts) * 4);
+		}
+		f.tables_bytes = off - f.tables_off;
+		total = off;
+		if (!pass)
+			HD_CUDA_TRY(cudaMalloc(&f.arena, total));
+	}
+	HD_CUDA_TRY(cudaMalloc(&f.dyn_dev, sizeof(FastDyn)));
+	HD_CUDA_TRY(cudaMalloc(&f.iota_dev, kFastMaxEdits * 4));
+	HD_CUDA_TRY(cudaMallocHost(&f.dyn_host, sizeof(FastDyn)));
+	HD_CUDA_TRY(cudaMallocHost(&f.ctr_host, sizeof(DevCounters)));
+	uint32_t iota[kFastMaxEdits];
+	for (uint32_t i = 0; i < kFastMaxEdits; ++i)
+		iota[i] = i;
+	HD_CUDA_TRY(cudaMemcpy(f.iota_dev, iota, sizeof(iota), cudaMemcpyHostToDevice));
+	memset(f.dyn_host, 0, sizeof(FastDyn));
+	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	const uint64_t before = g_launches.load();
+	HD_CUDA_TRY(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeRelaxed));
+	const hd_status es = fast_enqueue(p);
+	const cudaError_t ce = cudaStreamEndCapture(p->stream, &f.graph);
+	f.kernels = uint32_t(g_launches.load() - before);
+	g_launches.store(before); // captured, not launched
+	if (es != HD_OK)
+		return es;
+	HD_CUDA_TRY(ce);
+	HD_CUDA_TRY(cudaGraphInstantiate(&f.exec, f.graph, 0));
+	return HD_OK;
+}
+
+// Returns HD_OK with *handled = true when the call was served here; *handled = false sends it to the general path.
+static hd_status fast_edit(hd_pool *p, uint32_t root_in, const hd_edit_desc *edits, uint32_t n, uint32_t *root_out,
+                           hd_edit_stats *stats, bool *handled) {
+	*handled = false;
+	static const bool enabled = !(getenv("HD_EDIT_FAST") && atoi(getenv("HD_EDIT_FAST")) == 0);
+	EditScratch *s = p->edit;
+	FastPath &f = s->fast;
+	const uint32_t L = p->geo.node_levels;
+	if (!enabled || n > kFastMaxEdits || L < 2)
+		return HD_OK;
+	for (uint32_t i = 0; i < n; ++i) // terrain fills touch a large share of the world: always the general path
+		if (edits[i].kind == HD_EDIT_TERRAIN_FILL)
+			return HD_OK;
+	if (!f.tried) {
+		f.tried = true;
+		f.ok = fast_build(p) == HD_OK;
+		if (!f.ok) {
+			cudaGetLastError(); // e.g. no memory for the arena: the general path needs none of it
+			cudaStreamSynchronize(p->stream);
+		}
+	}
+	if (!f.ok)
+		return HD_OK;
+	f.dyn_host->root = root_in, f.dyn_host->n_edits = n;
+	memcpy(f.dyn_host->edits, edits, sizeof(hd_edit_desc) * n);
+	HD_CUDA_TRY(cudaGraphLaunch(f.exec, p->stream));
+	g_launches.fetch_add(f.kernels, std::memory_order_relaxed);
+	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	const DevCounters &c = *f.ctr_host;
+	if (c.error)
+		return HD_OK; // some queue was too small; nothing was written to the pool
+	*handled = true;
+	s->last_path = 1;
+	*root_out = c.root_out;
+	if (stats) {
+		memset(stats, 0, sizeof(*stats));
+		for (uint32_t l = 0; l + 1 < L; ++l)
+			stats->visited_nodes += c.lvl_items[l];
+		stats->visited_leaves = c.lvl_items[L - 1];
+		stats->upserts = c.stats[2], stats->appended_nodes = c.stats[3], stats->appended_words = c.stats[4];
+		stats->overflow_count = c.stats[5], stats->scan_words = c.stats[7];
+	}
+	return HD_OK;
+}
+
 } // namespace hd
 
 using namespace hd;
@@ -1191,6 +1418,14 @@ hd_status hd_edit_batch(hd_pool *p, uint32_t root_in, const hd_edit_desc *edits,
 		st = ensure_filled(p); // NodePool.hpp:408
 	if (st != HD_OK)
 		return st;
+	bool handled = false;
+	p->edit->last_path = 0;
+	st = fast_edit(p, root_in, edits, n, root_out, stats, &handled);
+	if (st != HD_OK || handled) {
+		if (st != HD_OK)
+			*root_out = root_in;
+		return st;
+	}
 	std::vector<LevelAlloc> levels;
 	hd_edit_desc *edits_dev = nullptr;
 	uint32_t *iota = nullptr;
@@ -1206,6 +1441,8 @@ hd_status hd_edit_batch(hd_pool *p, uint32_t root_in, const hd_edit_desc *edits,
 		*root_out = root_in;
 	return st;
 }
+
+uint32_t hd_edit_last_path(const hd_pool *p) { return p && p->edit ? p->edit->last_path : 0u; }
 
 hd_status hd_upsert_nodes(hd_pool *p, uint32_t level, const uint32_t *nodes, uint32_t words_each, uint32_t n,
                           uint32_t *out_ptrs) {

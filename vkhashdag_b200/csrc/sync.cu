@@ -34,10 +34,15 @@ __global__ void k_dirty_scan(const uint32_t *__restrict__ cur, const uint32_t *_
 	}
 }
 
-// one CTA per range at a time (grid-stride); n_ranges is read from the device header
-__global__ void k_dirty_gather(const uint32_t *__restrict__ words, const uint32_t *__restrict__ header,
-                               const uint32_t *__restrict__ ranges, uint32_t *payload) {
-	const uint32_t n = header[0];
+// one CTA per range at a time (grid-stride).  n_ranges comes from the device header; the triples start right behind
+// the header and the payload right behind the triples, so no host round trip separates the scan from the gather.
+// A staging buffer that cannot hold everything is left with its header only (the host sees the sizes and reports it).
+__global__ void k_dirty_gather(const uint32_t *__restrict__ words, uint32_t *stg, uint32_t cap_words) {
+	const uint32_t n = stg[0];
+	if (uint64_t(kHeaderWords) + uint64_t(n) * 3u + stg[1] > cap_words)
+		return;
+	const uint32_t *ranges = stg + kHeaderWords;
+	uint32_t *payload = stg + kHeaderWords + size_t(n) * 3u;
 	for (uint32_t r = blockIdx.x; r < n; r += gridDim.x) {
 		const uint32_t off = ranges[r * 3], cnt = ranges[r * 3 + 1], poff = ranges[r * 3 + 2];
 		for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
@@ -140,30 +145,30 @@ hd_status hd_dirty_pack_dev(hd_pool *p, void *staging_dev, uint64_t capacity_byt
 	if (!p || !staging_dev || !packed_bytes || capacity_bytes < kHeaderWords * 4)
 		return HD_ERR_INVALID;
 	HD_CUDA_TRY(cudaSetDevice(p->device));
+	// ONE pass, ONE host synchronisation (the interactive loop pays this every frame): the scan writes the range
+	// triples straight behind the header, the gather reads n_ranges from the device header to place the payload
+	// behind them, and only the 16-byte header comes back.  A staging buffer that turns out too small is reported
+	// with the size that is needed; nothing in the pool changes, so the caller grows the buffer and calls again.
+	uint32_t *stg = static_cast<uint32_t *>(staging_dev);
+	const uint64_t cap_words = std::min<uint64_t>(capacity_bytes / 4, 0xFFFFFFFFull);
+	const uint32_t cap_ranges = uint32_t((cap_words - kHeaderWords) / 3);
+	const uint32_t head[kHeaderWords] = {0u, 0u, p->root, p->needs_full_resync ? 1u : 0u}; // [3] = 1: clear first (after a GC)
+	HD_CUDA_TRY(cudaMemcpyAsync(stg, head, sizeof(head), cudaMemcpyHostToDevice, p->stream));
+	const uint32_t nb = p->geo.total_buckets;
+	k_dirty_scan<<<(nb + 255) / 256, 256, 0, p->stream>>>(p->bucket_words, p->bucket_synced, nb, p->geo.bucket_shift(), stg,
+	                                                      stg + kHeaderWords, cap_ranges);
+	HD_LAUNCH_CHECK();
+	k_dirty_gather<<<148u * 4u, 256, 0, p->stream>>>(p->words, stg, uint32_t(cap_words));
+	HD_LAUNCH_CHECK();
 	uint32_t h[kHeaderWords];
-	hd_status s = scan_counts(p, h);
-	if (s != HD_OK)
-		return s;
+	HD_CUDA_TRY(cudaMemcpyAsync(h, stg, sizeof(h), cudaMemcpyDeviceToHost, p->stream));
+	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
 	const uint64_t need = (uint64_t(kHeaderWords) + uint64_t(h[0]) * 3 + h[1]) * 4;
 	*packed_bytes = need;
 	if (need > capacity_bytes) {
 		set_error("staging buffer too small: need %llu bytes", (unsigned long long)need);
 		return HD_ERR_OVERFLOW;
 	}
-	uint32_t *stg = static_cast<uint32_t *>(staging_dev);
-	uint32_t *ranges = stg + kHeaderWords, *payload = ranges + size_t(h[0]) * 3;
-	HD_CUDA_TRY(cudaMemsetAsync(stg, 0, kHeaderWords * 4, p->stream));
-	const uint32_t nb = p->geo.total_buckets;
-	k_dirty_scan<<<(nb + 255) / 256, 256, 0, p->stream>>>(p->bucket_words, p->bucket_synced, nb, p->geo.bucket_shift(), stg,
-	                                                      ranges, h[0]);
-	HD_LAUNCH_CHECK();
-	if (h[0]) {
-		k_dirty_gather<<<std::min<uint32_t>(h[0], 148u * 8u), 256, 0, p->stream>>>(p->words, stg, ranges, payload);
-		HD_LAUNCH_CHECK();
-	}
-	const uint32_t tail[2] = {p->root, p->needs_full_resync ? 1u : 0u}; // [3] = 1: replicas clear before applying (after a GC)
-	HD_CUDA_TRY(cudaMemcpyAsync(stg + 2, tail, 8, cudaMemcpyHostToDevice, p->stream));
-	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
 	return HD_OK;
 }
 
@@ -231,8 +236,7 @@ hd_status hd_pool_save(hd_pool *p, const char *path) {
 	                                                      stg + kHeaderWords, h[0]);
 	HD_LAUNCH_CHECK();
 	if (h[0]) {
-		k_dirty_gather<<<std::min<uint32_t>(h[0], 148u * 8u), 256, 0, p->stream>>>(p->words, stg, stg + kHeaderWords,
-		                                                                          stg + kHeaderWords + size_t(h[0]) * 3);
+		k_dirty_gather<<<std::min<uint32_t>(h[0], 148u * 8u), 256, 0, p->stream>>>(p->words, stg, uint32_t(blob / 4));
 		HD_LAUNCH_CHECK();
 	}
 	std::vector<uint32_t> host(blob / 4);

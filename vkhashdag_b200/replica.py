@@ -35,17 +35,35 @@ def assemble_frame(parts, width, height, tile_w, tile_h, world, dtype=None):
     return frame
 
 
+class StagingTooSmall(Exception):
+    """DirtyPack could not fit the packed dirty ranges; `.need` is the size in bytes that would."""
+
+    def __init__(self, need):
+        super().__init__(f"staging buffer too small: need {need} bytes")
+        self.need = int(need)
+
+
 class ReplicaSync:
-    """Broadcast the editing rank's dirty ranges to every replica with one payload collective per edit batch."""
+    """Broadcast the editing rank's dirty ranges to every replica.
 
-    def __init__(self, pool, dist, device, capacity_bytes=64 << 20):
+    Latency matters here (the interactive loop publishes every frame), so the protocol spends ONE collective on the
+    common case: every publish broadcasts a fixed-size first chunk of the staging buffer (`eager_bytes`, the same on
+    every rank) that starts with the 16-byte header [n_ranges][payload_words][root][clear_first].  A brush edit's
+    dirty ranges (tens of bytes to tens of KB) fit in that chunk; only a larger payload (the initial replica copy, a
+    big batch) needs a second broadcast for the remainder, whose size the replicas learn from the header."""
+
+    def __init__(self, pool, dist, device, capacity_bytes=64 << 20, eager_bytes=256 << 10):
         self.pool, self.dist, self.device = pool, dist, device
-        self.staging = torch.empty(capacity_bytes, dtype=torch.uint8, device=device)
-        self.size = torch.zeros(1, dtype=torch.int64, device=device)
+        self.eager = max(16, min(int(eager_bytes), int(capacity_bytes)) & ~3)
+        self.staging = torch.empty(max(int(capacity_bytes), self.eager), dtype=torch.uint8, device=device)
+        self.collectives = 0   # payload collectives issued so far (tests / benches)
 
-    def _grow(self, need):
+    def _grow(self, need, keep=0):
         if need > self.staging.numel():
+            old = self.staging
             self.staging = torch.empty(int(need * 1.5), dtype=torch.uint8, device=self.device)
+            if keep:
+                self.staging[:keep].copy_(old[:keep])
 
     def publish(self, src=0):
         """Call on EVERY rank after rank `src` edited (and set its root).  Returns the packed size in bytes.
@@ -60,15 +78,22 @@ class ReplicaSync:
 
     def _publish(self, src):
         rank = self.dist.get_rank()
+        n = 0
         if rank == src:
-            _, need = self.pool.DirtyCount()
-            self._grow(need)
-            n = self.pool.DirtyPack(self.staging.data_ptr(), self.staging.numel())
-            self.size[0] = n
-        self.dist.broadcast(self.size, src)            # 8 bytes: lets replicas size the payload collective
-        n = int(self.size[0])
-        self._grow(n)
-        self.dist.broadcast(self.staging[:n], src)     # ONE payload broadcast (NCCL over NVLink on GPUs)
+            try:
+                n = self.pool.DirtyPack(self.staging.data_ptr(), self.staging.numel())
+            except StagingTooSmall as e:       # nothing changed in the pool: grow and pack again
+                self._grow(e.need)
+                n = self.pool.DirtyPack(self.staging.data_ptr(), self.staging.numel())
+        self.dist.broadcast(self.staging[:self.eager], src)   # header + (normally) the whole payload
+        self.collectives += 1
+        if rank != src:
+            head = self.staging[:16].view(torch.int32).cpu().numpy().view("uint32")
+            n = 4 * (4 + 3 * int(head[0]) + int(head[1]))
+        if n > self.eager:                                     # large payload: one more broadcast for the remainder
+            self._grow(n, keep=self.eager)
+            self.dist.broadcast(self.staging[self.eager:n], src)
+            self.collectives += 1
         if rank == src:
             self.pool.DirtyReset()
         else:
