@@ -174,10 +174,13 @@ hd_status hd_edit_batch(hd_pool *pool, uint32_t root_in, const hd_edit_desc *edi
  * nodes = n packed nodes, each `words_each` words (2 for a leaf level). out_ptrs[n]. */
 hd_status hd_upsert_nodes(hd_pool *pool, uint32_t level, const uint32_t *nodes, uint32_t words_each, uint32_t n,
                           uint32_t *out_ptrs);
-/* Which path served the last hd_edit_batch call on this pool: 1 = the low-latency path (batches of <= 32 sphere/AABB
- * editors — the interactive brush of src/main.cpp:214-238 — run as ONE pre-instantiated CUDA graph with device-resident
- * work-queue counts, one host round trip per call), 0 = the general level-synchronous path (any size; also taken when a
- * fixed-size work queue of the low-latency path would overflow, before anything is written).  Results are identical. */
+/* Which path served the last hd_edit_batch call on this pool.  0 = the general level-synchronous path (any batch size).
+ * 1 = the low-latency path: batches of <= 32 sphere/AABB editors — the interactive brush of src/main.cpp:214-238 — run as
+ * ONE cooperative kernel (grid barriers between levels, small levels walked by one CTA, work-queue counts resident on the
+ * device, parameters and counters through mapped host memory): one launch and one synchronisation per call.
+ * 2 = the same phases as a pre-instantiated CUDA graph (HD_EDIT_FAST=2).  HD_EDIT_FAST=0 disables 1 and 2.
+ * A fixed-size work queue that would overflow sends the call to the general path before anything is written.
+ * Results are identical on every path. */
 uint32_t hd_edit_last_path(const hd_pool *pool);
 
 /* ---- colour pool: the DAGColorPool buffers the tracer reads (src/DAGColorPool.hpp:43-52; bindings 1,2 of

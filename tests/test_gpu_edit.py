@@ -204,14 +204,14 @@ def test_brush_sequence_low_latency_path(oracle, hd):
     assert dev.last_stats["path"] == "general"          # terrain fills always take the general path
     for e in edits[1:]:
         groot = dev.EditBatch(groot, [e])
-        assert dev.last_stats["path"] == "graph" and dev.last_stats["overflow_count"] == 0
+        assert dev.last_stats["path"] == "fused" and dev.last_stats["overflow_count"] == 0
     exp = opool.canonical(oroot)
     got, _ = device_canonical(oracle, dev, cfg, groot)
     assert got["hash"] == exp["hash"] and got["by_ptr"] == got["by_content"] == exp["by_ptr"]
     assert got["voxels"] == exp["voxels"] and got["per_level"] == exp["per_level"]
     # a small multi-editor batch (<= 32) is one graph launch too, and order inside it is honoured
     g2 = dev.EditBatch(groot, edits[1:9])
-    assert dev.last_stats["path"] == "graph"
+    assert dev.last_stats["path"] == "fused"
     o2 = opool.edit_batch(oroot, edits[1:9])
     assert device_canonical(oracle, dev, cfg, g2)[0]["hash"] == opool.canonical(o2)["hash"]
     dev.close()
@@ -233,7 +233,7 @@ r = dev.EditBatch(abi.NULL, edits[:1])
 assert dev.last_stats["path"] == "general", dev.last_stats     # work queues of 64 items cannot hold this sphere
 used = dev.UsedWords()
 r = dev.EditBatch(r, edits[1:])
-assert dev.last_stats["path"] == "graph", dev.last_stats       # the small brush fits
+assert dev.last_stats["path"] == "fused", dev.last_stats       # the small brush fits
 mirror = O.pool(cfg)
 ranges, bw = dev.Download()
 for off, words in ranges.items():

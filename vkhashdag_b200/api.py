@@ -256,7 +256,7 @@ class DAGNodePool:
         st = HdEditStats()
         _check(self._L.hd_edit_batch(self._h, root, arr, len(arr), C.byref(out), C.byref(st)))
         self.last_stats = st.as_dict()
-        self.last_stats["path"] = "graph" if self._L.hd_edit_last_path(self._h) else "general"
+        self.last_stats["path"] = ("general", "fused", "graph")[self._L.hd_edit_last_path(self._h)]
         return out.value
 
     def Upsert(self, level, nodes, words_each):

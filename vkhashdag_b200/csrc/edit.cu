@@ -27,11 +27,14 @@
 #include "common.cuh"
 #include "editors.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
 namespace hd {
+namespace cg = cooperative_groups;
 
 constexpr uint32_t kPending = 0xFFFFFFFEu; // placeholder in child_new until the child item reports
 constexpr int kBlock = 256;
@@ -56,7 +59,7 @@ struct LevelView {
 	__device__ __forceinline__ uint32_t count() const {
 		if (!n_dev)
 			return n;
-		return *err_dev ? 0u : min(*n_dev, cap);
+		return *(volatile const uint32_t *)err_dev ? 0u : min(*(volatile const uint32_t *)n_dev, cap);
 	}
 	uint32_t cap;        // item capacity
 	uint32_t cap_entries;
@@ -88,16 +91,19 @@ struct FastDyn {
 struct FastPath {
 	bool tried = false, ok = false;
 	std::vector<LevelView> lv;
-	std::vector<uint32_t *> table;
-	std::vector<uint32_t> table_size;
 	char *arena = nullptr;
-	size_t tables_off = 0, tables_bytes = 0;
+	uint32_t *locks = nullptr; // one word per bucket (the reference stripes 1024 mutexes, src/DAGNodePool.hpp:43,56)
 	FastDyn *dyn_host = nullptr, *dyn_dev = nullptr;
 	DevCounters *ctr_host = nullptr;
 	uint32_t *iota_dev = nullptr;
 	cudaGraph_t graph = nullptr;
 	cudaGraphExec_t exec = nullptr;
 	uint32_t kernels = 0;
+	// mode 1 (default): the fused cooperative kernel; mode 2 (HD_EDIT_FAST=2): the same phases as a CUDA graph
+	int mode = 1;
+	FastDyn *dyn_host_dev = nullptr; // device-side addresses of the mapped host blocks
+	DevCounters *ctr_host_dev = nullptr;
+	uint32_t fused_grid = 0;
 };
 
 struct EditScratch {
@@ -305,17 +311,15 @@ __device__ inline uint2 warp_filter_write(const hd_edit_desc *__restrict__ edits
 
 // Root classification (edit_switch on the root, NodePool.hpp:405-413).  One warp.
 // `dyn` (low-latency path): {root, n_edits} live in device memory so that one instantiated graph serves every call.
-__global__ void k_root(Geometry g, const hd_edit_desc *__restrict__ edits, uint32_t n_edits,
-                       const uint32_t *__restrict__ iota, const uint32_t *__restrict__ filled, uint32_t root,
-                       LevelView out, DevCounters *ctr, const uint32_t *__restrict__ dyn) {
-	if (dyn)
-		root = dyn[0], n_edits = dyn[1];
+__device__ __forceinline__ void phase_root(const Geometry &g, const hd_edit_desc *__restrict__ edits, uint32_t n_edits,
+                                           const uint32_t *__restrict__ iota, const uint32_t *__restrict__ filled,
+                                           uint32_t root, const LevelView &out, DevCounters *ctr) {
 	const uint32_t bits = g.voxel_level();
 	const WarpFiltered f = warp_filter_count(edits, iota, n_edits, bits, 0, 0, 0, root, filled[0]);
 	uint2 r = make_uint2(0u, 0u);
 	if (f.count)
 		r = warp_filter_write(edits, iota, n_edits, bits, 0, 0, 0, f, filled[0], out.lists);
-	if (threadIdx.x != 0)
+	if ((threadIdx.x & 31u) != 0)
 		return;
 	if (r.y == 0) {
 		ctr->root_out = f.cur;
@@ -330,6 +334,13 @@ __global__ void k_root(Geometry g, const hd_edit_desc *__restrict__ edits, uint3
 	out.parent[0] = 0xFFFFFFFFu;
 	out.list_off[0] = r.x;
 	out.list_len[0] = r.y;
+}
+__global__ void k_root(Geometry g, const hd_edit_desc *__restrict__ edits, uint32_t n_edits,
+                       const uint32_t *__restrict__ iota, const uint32_t *__restrict__ filled, uint32_t root,
+                       LevelView out, DevCounters *ctr, const uint32_t *__restrict__ dyn) {
+	if (dyn)
+		root = dyn[0], n_edits = dyn[1];
+	phase_root(g, edits, n_edits, iota, filled, root, out, ctr);
 }
 
 // Top-down expansion of the (rare) items whose edit list is longer than 32: one warp per (item, child).
@@ -394,14 +405,16 @@ __global__ void __launch_bounds__(kBlock) k_down_long(Geometry g, uint32_t level
 
 // Top-down expansion: thread per (item, child); whole warps stride over the level (one trip when the host sized the
 // grid from a known item count, a grid-stride loop over the device-resident count on the low-latency path).
-__global__ void __launch_bounds__(kBlock) k_down(Geometry g, uint32_t level /* of `in` */,
-                                                 const uint32_t *__restrict__ words,
-                                                 const hd_edit_desc *__restrict__ edits,
-                                                 const uint32_t *__restrict__ filled, LevelView in, LevelView out,
-                                                 DevCounters *ctr, uint32_t *items_ctr, uint32_t *entries_ctr) {
+// (tid0, nthreads) = this thread's index among, and the number of, the threads that share the level: the whole grid, or
+// one CTA when the fused kernel walks a small level alone.
+__device__ __forceinline__ void phase_down(const Geometry &g, uint32_t level /* of `in` */,
+                                           const uint32_t *__restrict__ words, const hd_edit_desc *__restrict__ edits,
+                                           const uint32_t *__restrict__ filled, const LevelView &in, const LevelView &out,
+                                           DevCounters *ctr, uint32_t *items_ctr, uint32_t *entries_ctr, uint32_t tid0,
+                                           uint32_t nthreads) {
 	const uint32_t n8 = in.count() * 8u, lane = threadIdx.x & 31u;
 	const uint32_t bits = g.voxel_level() - (level + 1u);
-	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t - lane < n8; t += gridDim.x * blockDim.x) {
+	for (uint32_t t = tid0; t - lane < n8; t += nthreads) {
 		const uint32_t item = t >> 3, c = t & 7u;
 		const bool valid = t < n8;
 		Filtered f{kNull, 0u, 0u, 0u};
@@ -439,6 +452,13 @@ __global__ void __launch_bounds__(kBlock) k_down(Geometry g, uint32_t level /* o
 			in.child_new[size_t(item) * 8u + c] = f.cur;
 		}
 	}
+}
+__global__ void __launch_bounds__(kBlock) k_down(Geometry g, uint32_t level, const uint32_t *__restrict__ words,
+                                                 const hd_edit_desc *__restrict__ edits,
+                                                 const uint32_t *__restrict__ filled, LevelView in, LevelView out,
+                                                 DevCounters *ctr, uint32_t *items_ctr, uint32_t *entries_ctr) {
+	phase_down(g, level, words, edits, filled, in, out, ctr, items_ctr, entries_ctr, blockIdx.x * blockDim.x + threadIdx.x,
+	           gridDim.x * blockDim.x);
 }
 
 // Leaf pass: one warp per 4x4x4 leaf (a persistent grid-stride variant measured 10-20 % slower: the per-leaf work is
@@ -705,6 +725,317 @@ __global__ void __launch_bounds__(kBlock) k_upsert(Geometry g, uint32_t level, b
 		if (st_overflow)
 			atomicAdd(&ctr->stats[5], st_overflow);
 	}
+}
+
+// ---- low-latency path: fused bottom-up step ------------------------------------------------------------------------
+// One warp per work item does what k_leaf / k_assemble + k_dedup + k_upsert + k_resolve do in four launches: build the
+// item's new node, find-or-insert it, report the pointer to the parent.  Without a dedup phase two warps may carry equal
+// contents, so the insert is the reference's own threaded protocol (upsert_node<true>, NodePool.hpp:172-211): lock-free
+// find over [0, bucket_words), take the bucket's lock, re-find over what was appended meanwhile, append, publish
+// bucket_words, unlock.  Scans read through L2 (__ldcg: another SM's append is never hidden by a stale L1 line) and a
+// writer fences before it publishes bucket_words, so every word below a bucket_words value a scanner read is complete.
+__device__ __forceinline__ uint32_t warp_find(const uint32_t *words, uint32_t base, uint32_t from, uint32_t to,
+                                              const uint32_t *me /* shared */, uint32_t nw, bool is_leaf, bool fast_scan,
+                                              uint32_t wpp) {
+	const uint32_t lane = threadIdx.x & 31u, full = 0xFFFFFFFFu;
+	const uint32_t c0 = me[0], c1 = me[1];
+	uint32_t found = kNull;
+	if (is_leaf) {
+		for (uint32_t off = from & ~1u; off < to && found == kNull; off += 128u) {
+			uint2 w[2];
+#pragma unroll
+			for (int k = 0; k < 2; ++k) {
+				const uint32_t q = off + k * 64u + lane * 2u;
+				w[k] = q + 2u <= to ? __ldcg(reinterpret_cast<const uint2 *>(words + base + q)) : make_uint2(0u, 0u);
+			}
+#pragma unroll
+			for (int k = 0; k < 2; ++k) {
+				const uint32_t m = __ballot_sync(full, w[k].x == c0 && w[k].y == c1);
+				if (m && found == kNull)
+					found = base + off + k * 64u + (__ffs(m) - 1u) * 2u;
+			}
+		}
+	} else if (fast_scan) {
+		for (uint32_t off = from; off < to && found == kNull; off += 128u) {
+			uint32_t w[4];
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				const uint32_t q = off + k * 32u + lane;
+				w[k] = q + nw <= to ? __ldcg(words + base + q) : 0u;
+			}
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				const uint32_t q = off + k * 32u + lane;
+				bool hit = w[k] == c0; // c0 != 0: out-of-range slots (0) never match
+				if (hit)
+					for (uint32_t i = 1; i < nw && hit; ++i)
+						hit = __ldcg(words + base + q + i) == me[i];
+				const uint32_t m = __ballot_sync(full, hit);
+				if (m && found == kNull)
+					found = base + off + k * 32u + __ffs(m) - 1u;
+			}
+		}
+	} else {
+		if (lane == 0) { // tiny configs (a child pointer may look like a header): walk node by node, page by page
+			for (uint32_t it = from; it < to && found == kNull;) {
+				const uint32_t end = min((it | (wpp - 1u)) + 1u, to);
+				while (nw <= end - it) {
+					const uint32_t hw = __ldcg(words + base + it) & 0xFFu;
+					if (hw == 0u)
+						break;
+					const uint32_t sz = 1u + __popc(hw);
+					bool same = sz == nw;
+					for (uint32_t i = 0; i < nw && same; ++i)
+						same = __ldcg(words + base + it + i) == me[i];
+					if (same) {
+						found = base + it;
+						break;
+					}
+					it += sz;
+				}
+				it = end;
+			}
+		}
+		found = __shfl_sync(full, found, 0);
+	}
+	return found;
+}
+
+struct UpStats {
+	uint32_t upserts, nodes, words, overflow;
+	unsigned long long scan;
+};
+__device__ __forceinline__ uint32_t warp_upsert(const Geometry &g, uint32_t level, bool fast_scan, const uint32_t *me,
+                                                uint32_t nw, uint32_t fallback, uint32_t *words, uint32_t *bucket_words,
+                                                uint32_t *locks, UpStats &st) {
+	const uint32_t lane = threadIdx.x & 31u, full = 0xFFFFFFFFu;
+	const bool is_leaf = level == g.node_levels - 1u;
+	const uint32_t wpp = g.words_per_page(), wpb = g.words_per_bucket();
+	const uint32_t h = is_leaf ? hash_leaf(me[0], me[1]) : hash_inner(me, nw);
+	const uint32_t bucket = g.level_base[level] + (h & ((1u << g.bucket_bits[level]) - 1u)); // NodePool.hpp:163-164
+	const uint32_t base = bucket << g.bucket_shift();
+	volatile uint32_t *bwp = bucket_words + bucket;
+	const uint32_t bw = *bwp;
+	uint32_t found = warp_find(words, base, 0u, bw, me, nw, is_leaf, fast_scan, wpp);
+	st.upserts += 1, st.scan += bw;
+	if (found != kNull)
+		return found;
+	if (lane == 0) {
+		while (atomicCAS(locks + bucket, 0u, 1u) != 0u)
+			__nanosleep(32);
+		__threadfence();
+	}
+	__syncwarp(full);
+	const uint32_t bw2 = *bwp;
+	if (bw2 > bw) { // somebody appended between the scan and the lock: look at the new tail only (NodePool.hpp:187-192)
+		found = warp_find(words, base, bw, bw2, me, nw, is_leaf, fast_scan, wpp);
+		st.scan += bw2 - bw;
+	}
+	if (found == kNull) {
+		const uint32_t off = bw2 & (wpp - 1u);
+		const uint32_t at = off + nw > wpp ? (bw2 | (wpp - 1u)) + 1u : bw2; // never straddle a page; the tail stays zero
+		if (at + nw > wpb) { // bucket full: keep the old node (NodePool.hpp:137-139,195)
+			found = fallback;
+			st.overflow += 1;
+		} else {
+			if (lane < nw)
+				words[base + at + lane] = me[lane];
+			__threadfence();
+			__syncwarp(full);
+			if (lane == 0)
+				*bwp = at + nw;
+			found = base + at;
+			st.nodes += 1, st.words += at + nw - bw2;
+		}
+	}
+	__syncwarp(full);
+	if (lane == 0) {
+		__threadfence();
+		atomicExch(locks + bucket, 0u);
+	}
+	return found;
+}
+
+// One bottom-up level of the low-latency path.  Leaf level: the item's 64 voxels (k_leaf); inner levels: re-pack from
+// the children's reports (k_assemble).  Then find-or-insert and report to the parent's child slot.
+__device__ __forceinline__ void phase_up(const Geometry &g, uint32_t level, bool fast_scan, uint32_t *words,
+                                         uint32_t *bucket_words, uint32_t *locks, const hd_edit_desc *__restrict__ edits,
+                                         const LevelView &lv, uint32_t *parent_child_new, DevCounters *ctr,
+                                         uint32_t (*s_cand)[12], uint32_t tid0, uint32_t nthreads) {
+	const uint32_t lane = threadIdx.x & 31u, full = 0xFFFFFFFFu, n = lv.count();
+	const uint32_t warps = nthreads >> 5;
+	const bool is_leaf = level == g.node_levels - 1u;
+	uint32_t *me = s_cand[threadIdx.x >> 5];
+	UpStats st{0u, 0u, 0u, 0u, 0ull};
+	for (uint32_t item = tid0 >> 5; item < n; item += warps) {
+		const uint32_t cur = lv.cur[item];
+		uint32_t res = cur, nw = 0;
+		bool insert = false;
+		if (is_leaf) {
+			const uint32_t *list = lv.lists + lv.list_off[item];
+			const uint32_t len = lv.list_len[item];
+			uint32_t x, y, z;
+			unpack_pos(lv.pos[item], x, y, z);
+			uint32_t w0 = 0, w1 = 0;
+			if (cur != kNull) {
+				const uint2 w = *reinterpret_cast<const uint2 *>(words + cur);
+				w0 = w.x, w1 = w.y;
+			}
+			const uint32_t vx = (x << 2) | ((lane >> 2) & 2u) | (lane & 1u);
+			const uint32_t vy = (y << 2) | ((lane >> 3) & 2u) | ((lane >> 1) & 1u);
+			const uint32_t vz = (z << 2) | ((lane >> 2) & 1u);
+			bool a = w0 >> lane & 1u, b = w1 >> lane & 1u;
+			for (uint32_t j = 0; j < len; ++j) {
+				const hd_edit_desc &e = edits[list[j]];
+				a = edit_voxel(e, vx, vy, vz, a);
+				b = edit_voxel(e, vx, vy, vz + 2u, b);
+			}
+			const uint32_t n0 = __ballot_sync(full, a), n1 = __ballot_sync(full, b);
+			if (n0 != w0 || n1 != w1) {
+				if ((n0 | n1) == 0u)
+					res = kNull;
+				else {
+					insert = true, nw = 2;
+					if (lane == 0)
+						me[0] = n0, me[1] = n1;
+				}
+			}
+		} else {
+			uint32_t newc = kNull, oldc = kNull;
+			if (lane < 8u) {
+				newc = lv.child_new[size_t(item) * 8u + lane];
+				if (cur != kNull) {
+					const uint32_t old_mask = words[cur];
+					if (old_mask >> lane & 1u)
+						oldc = words[cur + 1u + __popc(old_mask & ((1u << lane) - 1u))];
+				}
+			}
+			const uint32_t changed = __ballot_sync(full, newc != oldc);
+			const uint32_t mask = __ballot_sync(full, newc != kNull);
+			if (changed) {
+				if (mask == 0u)
+					res = kNull;
+				else {
+					insert = true, nw = 1u + __popc(mask);
+					if (lane == 0)
+						me[0] = mask;
+					if (newc != kNull)
+						me[1u + __popc(mask & ((1u << lane) - 1u))] = newc;
+				}
+			}
+		}
+		if (insert) {
+			__syncwarp(full);
+			res = warp_upsert(g, level, fast_scan, me, nw, cur, words, bucket_words, locks, st);
+			__syncwarp(full);
+		}
+		if (lane == 0) {
+			const uint32_t par = lv.parent[item];
+			if (par == 0xFFFFFFFFu)
+				ctr->root_out = res;
+			else
+				parent_child_new[par] = res;
+		}
+	}
+	if (lane == 0 && st.upserts) {
+		atomicAdd(&ctr->stats[2], (unsigned long long)st.upserts);
+		atomicAdd(&ctr->stats[7], st.scan);
+		if (st.nodes) {
+			atomicAdd(&ctr->stats[3], (unsigned long long)st.nodes);
+			atomicAdd(&ctr->stats[4], (unsigned long long)st.words);
+		}
+		if (st.overflow)
+			atomicAdd(&ctr->stats[5], (unsigned long long)st.overflow);
+	}
+}
+__global__ void __launch_bounds__(kBlock) k_up(Geometry g, uint32_t level, bool fast_scan, uint32_t *words,
+                                               uint32_t *bucket_words, uint32_t *locks,
+                                               const hd_edit_desc *__restrict__ edits, LevelView lv,
+                                               uint32_t *parent_child_new, DevCounters *ctr) {
+	__shared__ uint32_t s_cand[kBlock / 32][12];
+	phase_up(g, level, fast_scan, words, bucket_words, locks, edits, lv, parent_child_new, ctr, s_cand,
+	         blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+// The whole rebuild of a small batch in ONE cooperative launch: grid-wide barriers separate the levels, and the levels
+// that hold only a handful of items (every level above the brush's footprint: 10-12 of 16 at 2^17) are walked by CTA 0
+// alone with __syncthreads between them, so they cost a block barrier instead of a launch or a grid barrier each.
+// Call parameters come in through mapped host memory and the counters go back the same way: no copy commands at all.
+constexpr int kFusedThreads = 512;
+constexpr uint32_t kSoloDown = 128; // items one CTA expands alone (8 threads per item)
+constexpr uint32_t kSoloUp = 32;    // items one CTA finishes alone (one warp per item)
+struct FusedArgs {
+	Geometry g;
+	uint32_t *words, *bucket_words, *locks;
+	const uint32_t *iota, *filled;
+	const FastDyn *dyn_host; // mapped pinned host memory
+	FastDyn *dyn_dev;
+	DevCounters *ctr, *ctr_host; // ctr_host: mapped pinned host memory
+	LevelView lv[HD_MAX_NODE_LEVELS];
+	bool fast_scan;
+};
+__global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_constant__ FusedArgs a) {
+	__shared__ uint32_t s_cand[kFusedThreads / 32][12];
+	__shared__ uint32_t s_first_big;
+	cg::grid_group grid = cg::this_grid();
+	const Geometry &g = a.g;
+	const uint32_t L = g.node_levels;
+	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+	DevCounters *ctr = a.ctr;
+	const hd_edit_desc *edits = a.dyn_dev->edits;
+	volatile uint32_t *items = ctr->lvl_items;
+
+	// ---- stage A (CTA 0): fetch the call, classify the root, walk the small top levels ----
+	if (blockIdx.x == 0) {
+		for (uint32_t i = threadIdx.x; i < sizeof(DevCounters) / 4; i += blockDim.x)
+			reinterpret_cast<uint32_t *>(ctr)[i] = 0u;
+		for (uint32_t i = threadIdx.x; i < sizeof(FastDyn) / 4; i += blockDim.x)
+			reinterpret_cast<uint32_t *>(a.dyn_dev)[i] = reinterpret_cast<const volatile uint32_t *>(a.dyn_host)[i];
+		__syncthreads();
+		if (threadIdx.x < 32)
+			phase_root(g, edits, a.dyn_dev->n_edits, a.iota, a.filled, a.dyn_dev->root, a.lv[0], ctr);
+		__syncthreads();
+		uint32_t l = 0;
+		for (; l + 1 < L && items[l] <= kSoloDown; ++l) {
+			phase_down(g, l, a.words, edits, a.filled, a.lv[l], a.lv[l + 1], ctr, &ctr->lvl_items[l + 1], &ctr->lvl_entries[l + 1],
+			           threadIdx.x, blockDim.x);
+			__syncthreads();
+		}
+		if (threadIdx.x == 0)
+			ctr->next_items = l; // first level the whole grid expands
+	}
+	grid.sync();
+	// ---- stage B (grid): the remaining top-down levels ----
+	for (uint32_t l = *(volatile uint32_t *)&ctr->next_items; l + 1 < L; ++l) {
+		phase_down(g, l, a.words, edits, a.filled, a.lv[l], a.lv[l + 1], ctr, &ctr->lvl_items[l + 1], &ctr->lvl_entries[l + 1], gtid,
+		           gthreads);
+		grid.sync();
+	}
+	// ---- stage C (grid): bottom-up over the levels that are worth the grid; then CTA 0 finishes the small top ----
+	if (threadIdx.x == 0) {
+		uint32_t solo = 0; // levels [0, solo) are small all the way up
+		while (solo < L && items[solo] <= kSoloUp)
+			++solo;
+		s_first_big = solo;
+	}
+	__syncthreads();
+	const uint32_t solo = s_first_big;
+	for (uint32_t l = L; l-- > solo;) {
+		phase_up(g, l, a.fast_scan, a.words, a.bucket_words, a.locks, edits, a.lv[l], l ? a.lv[l - 1].child_new : nullptr, ctr, s_cand,
+		         gtid, gthreads);
+		grid.sync();
+	}
+	if (blockIdx.x != 0)
+		return;
+	for (uint32_t l = solo; l-- > 0;) {
+		phase_up(g, l, a.fast_scan, a.words, a.bucket_words, a.locks, edits, a.lv[l], l ? a.lv[l - 1].child_new : nullptr, ctr, s_cand,
+		         threadIdx.x, blockDim.x);
+		__syncthreads();
+	}
+	__threadfence();
+	for (uint32_t i = threadIdx.x; i < sizeof(DevCounters) / 4; i += blockDim.x)
+		reinterpret_cast<volatile uint32_t *>(a.ctr_host)[i] = __ldcg(reinterpret_cast<const uint32_t *>(ctr) + i);
+	__threadfence_system();
 }
 
 // Losers copy their winner's pointer; every item reports to its parent's child slot (or the root output).
@@ -1248,7 +1579,6 @@ static hd_status fast_enqueue(hd_pool *p) {
 	const uint32_t L = g.node_levels;
 	HD_CUDA_TRY(cudaMemcpyAsync(f.dyn_dev, f.dyn_host, sizeof(FastDyn), cudaMemcpyHostToDevice, st));
 	HD_CUDA_TRY(cudaMemsetAsync(s->ctr, 0, sizeof(DevCounters), st));
-	HD_CUDA_TRY(cudaMemsetAsync(f.arena + f.tables_off, 0, f.tables_bytes, st));
 	k_root<<<1, 32, 0, st>>>(g, f.dyn_dev->edits, 0, f.iota_dev, s->filled_dev, 0, f.lv[0], s->ctr, &f.dyn_dev->root);
 	HD_LAUNCH_CHECK();
 	for (uint32_t l = 0; l + 1 < L; ++l) {
@@ -1259,19 +1589,8 @@ static hd_status fast_enqueue(hd_pool *p) {
 	}
 	for (uint32_t l = L; l-- > 0;) {
 		const LevelView &v = f.lv[l];
-		const bool leaf = l == L - 1;
-		if (leaf)
-			k_leaf<<<fast_grid(p, uint64_t(v.cap) * 32), kBlock, 0, st>>>(g, p->words, f.dyn_dev->edits, v, s->ctr);
-		else
-			k_assemble<<<fast_grid(p, v.cap), kBlock, 0, st>>>(p->words, v);
-		HD_LAUNCH_CHECK();
-		k_dedup<<<fast_grid(p, v.cap), kBlock, 0, st>>>(0, leaf ? 2 : 9, leaf, v.cand, v.state, v.winner, f.table[l],
-		                                               f.table_size[l] - 1, v.n_dev, v.err_dev);
-		HD_LAUNCH_CHECK();
-		k_upsert<<<fast_grid(p, uint64_t(v.cap) * 32), kBlock, 0, st>>>(g, l, s->fast_scan, 0, leaf ? 2 : 9, v.cand, v.state, v.cur,
-		                                                              v.result, p->words, p->bucket_words, s->ctr, v.n_dev);
-		HD_LAUNCH_CHECK();
-		k_resolve<<<fast_grid(p, v.cap), kBlock, 0, st>>>(v, l ? f.lv[l - 1].child_new : nullptr, s->ctr);
+		k_up<<<fast_grid(p, uint64_t(v.cap) * 32), kBlock, 0, st>>>(g, l, s->fast_scan, p->words, p->bucket_words, f.locks,
+		                                                          f.dyn_dev->edits, v, l ? f.lv[l - 1].child_new : nullptr, s->ctr);
 		HD_LAUNCH_CHECK();
 	}
 	HD_CUDA_TRY(cudaMemcpyAsync(f.ctr_host, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
@@ -1285,7 +1604,6 @@ static hd_status fast_build(hd_pool *p) {
 	const uint32_t L = g.node_levels;
 	static const uint32_t cap_max = getenv("HD_EDIT_FAST_CAP") ? uint32_t(atoi(getenv("HD_EDIT_FAST_CAP"))) : (1u << 18);
 	f.lv.assign(L, LevelView{});
-	f.table.assign(L, nullptr), f.table_size.assign(L, 0);
 	// pass 1 sizes the arena, pass 2 hands out the pointers
 	size_t total = 0;
 	for (int pass = 0; pass < 2; ++pass) {
@@ -1305,35 +1623,41 @@ static hd_status fast_build(hd_pool *p) {
 			v.n_dev = &s->ctr->lvl_items[l], v.err_dev = &s->ctr->error;
 			v.cur = (uint32_t *)take(size_t(cap) * 4), v.pos = (uint64_t *)take(size_t(cap) * 8);
 			v.list_off = (uint32_t *)take(size_t(cap) * 4), v.list_len = (uint32_t *)take(size_t(cap) * 4);
-			v.parent = (uint32_t *)take(size_t(cap) * 4), v.result = (uint32_t *)take(size_t(cap) * 4);
-			v.winner = (uint32_t *)take(size_t(cap) * 4), v.state = (uint8_t *)take(cap);
+			v.parent = (uint32_t *)take(size_t(cap) * 4);
 			v.lists = (uint32_t *)take(size_t(cap_e) * 4);
-			v.cand = (uint32_t *)take(size_t(cap) * (leaf ? 2 : 9) * 4);
 			v.child_new = leaf ? nullptr : (uint32_t *)take(size_t(cap) * 8 * 4);
 		}
-		f.tables_off = off;
-		for (uint32_t l = 0; l < L; ++l) { // the dedup tables are contiguous: one memset clears them all
-			uint32_t ts = 64;
-			while (ts < f.lv[l].cap * 2u)
-				ts <<= 1;
-			f.table_size[l] = ts;
-			f.table[l] = (uint32_t *)take(size_t(ts) * 4);
-		}
-		f.tables_bytes = off - f.tables_off;
+		f.locks = (uint32_t *)take(size_t(g.total_buckets) * 4);
 		total = off;
-		if (!pass)
+		if (!pass) {
 			HD_CUDA_TRY(cudaMalloc(&f.arena, total));
+			HD_CUDA_TRY(cudaMemset(f.arena, 0, total)); // the bucket locks start (and always end) released
+		}
 	}
 	HD_CUDA_TRY(cudaMalloc(&f.dyn_dev, sizeof(FastDyn)));
 	HD_CUDA_TRY(cudaMalloc(&f.iota_dev, kFastMaxEdits * 4));
-	HD_CUDA_TRY(cudaMallocHost(&f.dyn_host, sizeof(FastDyn)));
-	HD_CUDA_TRY(cudaMallocHost(&f.ctr_host, sizeof(DevCounters)));
+	HD_CUDA_TRY(cudaHostAlloc(&f.dyn_host, sizeof(FastDyn), cudaHostAllocMapped));
+	HD_CUDA_TRY(cudaHostAlloc(&f.ctr_host, sizeof(DevCounters), cudaHostAllocMapped));
+	HD_CUDA_TRY(cudaHostGetDevicePointer(&f.dyn_host_dev, f.dyn_host, 0));
+	HD_CUDA_TRY(cudaHostGetDevicePointer(&f.ctr_host_dev, f.ctr_host, 0));
 	uint32_t iota[kFastMaxEdits];
 	for (uint32_t i = 0; i < kFastMaxEdits; ++i)
 		iota[i] = i;
 	HD_CUDA_TRY(cudaMemcpy(f.iota_dev, iota, sizeof(iota), cudaMemcpyHostToDevice));
 	memset(f.dyn_host, 0, sizeof(FastDyn));
 	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	f.mode = getenv("HD_EDIT_FAST") && atoi(getenv("HD_EDIT_FAST")) == 2 ? 2 : 1;
+	if (f.mode == 1) {
+		int coop = 0, per_sm = 0, sms = 0;
+		HD_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
+		HD_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device));
+		HD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_edit_fused, kFusedThreads, 0));
+		if (coop && per_sm > 0) {
+			f.fused_grid = uint32_t(sms) * uint32_t(std::min(per_sm, 2));
+			return HD_OK;
+		}
+		f.mode = 2; // no cooperative launch on this device: same phases as a graph
+	}
 	const uint64_t before = g_launches.load();
 	HD_CUDA_TRY(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeRelaxed));
 	const hd_status es = fast_enqueue(p);
@@ -1351,7 +1675,7 @@ static hd_status fast_build(hd_pool *p) {
 static hd_status fast_edit(hd_pool *p, uint32_t root_in, const hd_edit_desc *edits, uint32_t n, uint32_t *root_out,
                            hd_edit_stats *stats, bool *handled) {
 	*handled = false;
-	static const bool enabled = !(getenv("HD_EDIT_FAST") && atoi(getenv("HD_EDIT_FAST")) == 0);
+	static const bool enabled = !(getenv("HD_EDIT_FAST") && atoi(getenv("HD_EDIT_FAST")) == 0); // 0 general, 1 fused, 2 graph
 	EditScratch *s = p->edit;
 	FastPath &f = s->fast;
 	const uint32_t L = p->geo.node_levels;
@@ -1372,14 +1696,30 @@ static hd_status fast_edit(hd_pool *p, uint32_t root_in, const hd_edit_desc *edi
 		return HD_OK;
 	f.dyn_host->root = root_in, f.dyn_host->n_edits = n;
 	memcpy(f.dyn_host->edits, edits, sizeof(hd_edit_desc) * n);
-	HD_CUDA_TRY(cudaGraphLaunch(f.exec, p->stream));
-	g_launches.fetch_add(f.kernels, std::memory_order_relaxed);
+	if (f.mode == 1) {
+		FusedArgs a{};
+		a.g = p->geo;
+		a.words = p->words, a.bucket_words = p->bucket_words, a.locks = f.locks;
+		a.iota = f.iota_dev, a.filled = s->filled_dev;
+		a.dyn_host = f.dyn_host_dev, a.dyn_dev = f.dyn_dev;
+		a.ctr = s->ctr, a.ctr_host = f.ctr_host_dev;
+		for (uint32_t l = 0; l < L; ++l)
+			a.lv[l] = f.lv[l];
+		a.fast_scan = s->fast_scan;
+		void *params[] = {&a};
+		HD_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_edit_fused, dim3(f.fused_grid), dim3(kFusedThreads), params, 0,
+		                                        p->stream));
+		g_launches.fetch_add(1, std::memory_order_relaxed);
+	} else {
+		HD_CUDA_TRY(cudaGraphLaunch(f.exec, p->stream));
+		g_launches.fetch_add(f.kernels, std::memory_order_relaxed);
+	}
 	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
 	const DevCounters &c = *f.ctr_host;
 	if (c.error)
 		return HD_OK; // some queue was too small; nothing was written to the pool
 	*handled = true;
-	s->last_path = 1;
+	s->last_path = uint32_t(f.mode);
 	*root_out = c.root_out;
 	if (stats) {
 		memset(stats, 0, sizeof(*stats));
