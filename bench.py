@@ -27,6 +27,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W4K, H4K = 3840, 2160
+EDIT_BATCH = 10000        # sphere edits of the secondary metric (BASELINE.json config 3)
+CFG3_BUCKET_BITS = [10] * 9 + [16] * 4 + [18] * 3   # bucket bits per node level of the 2^17 pool
+CFG3_PATCH_BITS = 15
 LEVEL_COUNT = 15          # 2^15 voxels per axis
 BOTTOM_BUCKET_BITS = 17   # DefaultConfig with 2^17 buckets per bottom level: the default 2^16 overflows level 12
 TILE = 64
@@ -293,6 +296,47 @@ def run_ours(args):
     if rank == 0 and n == 1 and not args.no_cpu_baseline:
         cpu_baseline = cpu_baseline_leg(pool, cfg, root, args)
 
+    # ---- secondary metric of BASELINE.json: "edited voxels/s per batch" on config 3 (2^17 world, 2^15 terrain patch,
+    # 10 000 random sphere fill/dig edits in index order) and the latency of one brush edit per call; N = 1 only ----
+    if rank == 0 and n == 1:
+        cfg3 = abi.custom_config(CFG3_BUCKET_BITS)
+        vl3 = cfg3.voxel_level
+        pool3 = v.DAGNodePool(cfg3, device=local)
+        root3 = pool3.Edit(abi.NULL, v.TerrainEditor(vl3, extent_bits=CFG3_PATCH_BITS))
+        assert pool3.last_stats["overflow_count"] == 0
+        spheres = abi.random_spheres(EDIT_BATCH, vl3, seed=1234, rmin=16, rmax=256, extent_bits=CFG3_PATCH_BITS)
+        mirror = pool3.Download() if cpu_baseline is not None else None   # un-edited scene for the CPU editor (timed later)
+        arr = abi.edit_array(spheres)
+        # the GPU idled while the host worked (CPU tracer leg, descriptor set-up): bring the clocks back up with a few
+        # untimed frames before the 0.1 s batch is timed
+        P3 = abi.camera_params(cfg3, root3, (0.06, 0.09, 0.06), 0.8, -0.5236, W4K, H4K, lod=False)
+        with torch.cuda.stream(torch.cuda.ExternalStream(pool3.stream, device=local)):
+            for _ in range(40):
+                pool3.TraceDev(P3, rgba8=rgba.data_ptr())
+            pool3.Sync()
+        t0 = time.perf_counter()
+        root_b = pool3.EditBatch(root3, arr)
+        dt = time.perf_counter() - t0
+        st = pool3.last_stats
+        assert st["overflow_count"] == 0, "bucket overflow in the edit batch: parity void"
+        in_range = abi.spheres_in_range_voxels(spheres, vl3)
+        edit["batch"] = {"workload": f"cfg3: 2^{vl3} world, 2^{CFG3_PATCH_BITS} terrain patch, {EDIT_BATCH} random sphere fill/dig edits "
+                                     f"(r 16..256, xorshift32 seed 1234), one hd_edit_batch call", "seconds": round(dt, 4),
+                         "edited_voxels_per_s": round(in_range / dt), "in_range_voxels": in_range,
+                         "visited_leaves": st["visited_leaves"], "appended_nodes": st["appended_nodes"], "path": st["path"]}
+        ms = []
+        for e in abi.random_spheres(60, vl3, seed=77, rmin=128, rmax=128, extent_bits=CFG3_PATCH_BITS):
+            a1 = abi.edit_array([e])
+            t0 = time.perf_counter()
+            root_b = pool3.EditBatch(root_b, a1)
+            ms.append((time.perf_counter() - t0) * 1e3)
+            assert pool3.last_stats["overflow_count"] == 0
+        edit["brush"] = {"workload": "one r=128 sphere brush per hd_edit_batch call on the edited cfg3 scene (60 calls, fill/dig alternating)",
+                         "ms_per_edit_median": round(float(np.median(ms[5:])), 4), "path": pool3.last_stats["path"]}
+        if mirror is not None:
+            cpu_baseline["edit"] = cpu_edit_leg(mirror, cfg3, root3, spheres[:40])
+        pool3.close()
+
     if rank == 0:
         line = {
             "metric": "Mrays/s primary-ray traversal @4K", "value": round(value, 2), "unit": "Mrays/s", "n_gpus": n,
@@ -355,6 +399,30 @@ def cpu_baseline_leg(pool, cfg, root, args):
             "sample": f"every {row_step}th row of {frames} 4K frames ({rays} rays/frame), full detail, "
                       f"{'NodePoolTraversal::Traversal<float>' if kind == 'reference' else 'oracle port'} on {cores} threads",
             "words_per_ray_F_sample": round(fr["fetches"] / rays, 3)}
+
+
+def cpu_edit_leg(mirror, cfg3, root3, sample):
+    """The reference's CPU editor on the first spheres of the cfg3 edit list: the GPU-built terrain pool is mirrored
+    into the CPU pool, then one call per edit — ThreadedEdit on all host cores with max_task_level = 10 as in
+    src/main.cpp:216 (oracle/_ref), or the serial Edit port when the reference could not be compiled."""
+    from oracle import bindings as B
+    from vkhashdag_b200 import abi
+    cores = os.cpu_count() or 1
+    kind = "reference" if B.Ref.available() else "port"
+    host = (B.Ref() if kind == "reference" else B.Oracle()).pool(cfg3)
+    ranges, bw = mirror
+    for off, words in ranges.items():
+        host.words_np(off, len(words))[:] = words
+    host.bucket_words_np()[:] = bw
+    hroot = root3
+    t = time.perf_counter()
+    for e in sample:
+        hroot = host.edit(hroot, e, threads=cores, max_task_level=10) if kind == "reference" else host.edit(hroot, e)
+    dt = time.perf_counter() - t
+    return {"edits": len(sample), "seconds": round(dt, 4), "ms_per_edit": round(dt / len(sample) * 1e3, 4),
+            "edited_voxels_per_s": round(abi.spheres_in_range_voxels(sample, cfg3.voxel_level) / dt), "kind": kind, "cores": cores,
+            "what": "ThreadedEdit(busy_pool(cores), max_task_level=10), one call per edit, first 40 edits of the batch"
+                    if kind == "reference" else "serial Edit port, first 40 edits of the batch"}
 
 
 # --------------------------------------------------------------------------------------------- reference arm

@@ -94,3 +94,12 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "from oracle" not in text and "import oracle" not in text and "liboracle" not in text, f
+
+
+def test_host_in_range_voxel_count_matches_oracle(oracle):
+    """abi.spheres_in_range_voxels (the unit bench.py reports edited voxels/s in) == the oracle's lattice count,
+    including balls clipped by the world in x, y and z."""
+    from vkhashdag_b200 import abi
+    for vl, kw in ((12, {}), (10, dict(rmin=3, rmax=200)), (8, dict(rmin=60, rmax=200, y_lo=0, y_hi=256))):
+        sp = abi.random_spheres(60, vl, seed=7, **kw)
+        assert abi.spheres_in_range_voxels(sp, vl) == sum(oracle.in_range_voxels(s, vl) for s in sp)

@@ -1,0 +1,23 @@
+#!/bin/bash
+# second profiling pass of round 1 (run on the GPU box): full bench line, reference arm, launch lists and ncu --set full
+# captures of the new edit kernels.  Outputs under gpurun_out/.
+mkdir -p gpurun_out
+python bench.py > gpurun_out/bench_r1b.json 2> gpurun_out/bench_r1b.err
+tail -c 600 gpurun_out/bench_r1b.err
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r1b_reference.json 2>> gpurun_out/bench_r1b.err
+BB=10,10,10,10,10,10,10,10,10,16,16,16,16,18,18,18
+# launch list of the cfg3 batch (terrain build + one 10k-sphere batch)
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r1b_edit.csv \
+    python tools/bench_edit.py --cpu-sample 1 --bucket-bits $BB > gpurun_out/ncu_edit_r1b.log 2>&1
+# launch list of the brush loop (fused kernel, one launch per edit)
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r1b_brush.csv \
+    python tools/bench_brush.py --radii 2,32,128,256 --edits 12 --cpu-sample 0 > gpurun_out/ncu_brush_r1b.log 2>&1
+# full captures: fused brush kernel (r = 128), grouped upsert + leaf + down kernels of the batch
+ncu --set full --clock-control none --import-source on -k regex:k_edit_fused -s 8 -c 2 -o gpurun_out/brush_r1b \
+    python tools/bench_brush.py --radii 128 --edits 12 --cpu-sample 0 >> gpurun_out/ncu_brush_r1b.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_upsert_grouped|k_leaf|k_down$' -s 24 -c 8 -o gpurun_out/edit_r1b \
+    python tools/bench_edit.py --cpu-sample 1 --bucket-bits $BB >> gpurun_out/ncu_edit_r1b.log 2>&1
+for f in brush_r1b edit_r1b; do
+  ncu -i gpurun_out/$f.ncu-rep --page raw --csv > gpurun_out/${f}_raw.csv 2>/dev/null
+done
+ls -la gpurun_out | tail -20

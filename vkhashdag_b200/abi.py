@@ -145,6 +145,45 @@ def random_spheres(n, voxel_level, seed=1234, rmin=16, rmax=256, y_lo=None, y_hi
     return out
 
 
+
+def spheres_in_range_voxels(spheres, voxel_level):
+    """Sum over sphere edits of |{v in world : VoxelInRange(v)}| (main.cpp:127-132) — the implementation-independent
+    "edited voxels" unit of SURVEY §8d — computed on the host from the definition: per distinct r2 a table of y-column
+    lengths over (dx, dz) with 2-D prefix sums, clipped per sphere to the world in x and z (y is clipped per column)."""
+    res = 1 << voxel_level
+    tables = {}
+    total = 0
+    for e in spheres:
+        r2 = int(e.r2)
+        cx, cy, cz = int(e.p0[0]), int(e.p0[1]), int(e.p0[2])
+        r = int(np.sqrt(float(r2)))
+        while (r + 1) * (r + 1) <= r2:
+            r += 1
+        while r * r > r2:
+            r -= 1
+        unclipped_y = cy - r >= 0 and cy + r < res
+        key = (r2, unclipped_y and 0 or cy)  # y clipping depends on cy only when the ball pokes out of the world in y
+        if key not in tables:
+            d = np.arange(-r, r + 1, dtype=np.int64)
+            rem = r2 - d[:, None] ** 2 - d[None, :] ** 2
+            half = np.floor(np.sqrt(np.maximum(rem, 0).astype(np.float64))).astype(np.int64)
+            half = np.where((half + 1) ** 2 <= rem, half + 1, half)
+            half = np.where(half ** 2 > rem, half - 1, half)
+            lo = np.maximum(cy - half, 0) if not unclipped_y else cy - half
+            hi = np.minimum(cy + half, res - 1) if not unclipped_y else cy + half
+            col = np.where(rem >= 0, np.maximum(hi - lo + 1, 0), 0)
+            ps = np.zeros((2 * r + 2, 2 * r + 2), dtype=np.int64)
+            ps[1:, 1:] = col.cumsum(0).cumsum(1)
+            tables[key] = ps
+        ps = tables[key]
+        x0, x1 = max(-r, -cx), min(r, res - 1 - cx)
+        z0, z1 = max(-r, -cz), min(r, res - 1 - cz)
+        if x0 > x1 or z0 > z1:
+            continue
+        a0, a1, b0, b1 = x0 + r, x1 + r + 1, z0 + r, z1 + r + 1
+        total += int(ps[a1, b1] - ps[a0, b1] - ps[a1, b0] + ps[a0, b0])
+    return total
+
 def camera_params(cfg, root, pos, yaw, pitch, width, height, fov=np.pi / 3, color_root=COLOR_NULL,
                   color_leaf_level=10, type_=0, lod=True):
     """Push-constant block as src/rg/TracePass.cpp:106-134 + src/Camera.hpp:36-52 build it (float32 host maths)."""

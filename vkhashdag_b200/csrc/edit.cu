@@ -485,6 +485,11 @@ __global__ void __launch_bounds__(kBlock) k_leaf(Geometry g, const uint32_t *__r
 		bool a = w0 >> lane & 1u, b = w1 >> lane & 1u;
 		for (uint32_t j = 0; j < len; ++j) {
 			const hd_edit_desc &e = edits[list[j]];
+			bool ia, ib;
+			if (e.kind == HD_EDIT_TERRAIN_FILL && terrain_leaf_pair(e, x << 2, z << 2, vx, vy, vz, ia, ib)) { // warp-uniform
+				a = a || ia, b = b || ib;
+				continue;
+			}
 			a = edit_voxel(e, vx, vy, vz, a);
 			b = edit_voxel(e, vx, vy, vz + 2u, b);
 		}
@@ -767,9 +772,15 @@ __device__ __forceinline__ uint32_t warp_find(const uint32_t *words, uint32_t ba
 			for (int k = 0; k < 4; ++k) {
 				const uint32_t q = off + k * 32u + lane;
 				bool hit = w[k] == c0; // c0 != 0: out-of-range slots (0) never match
-				if (hit)
-					for (uint32_t i = 1; i < nw && hit; ++i)
-						hit = __ldcg(words + base + q + i) == me[i];
+				if (hit) { // header match (rare unless it is the node): all child words in flight at once, then compare
+					uint32_t v[8];
+#pragma unroll
+					for (uint32_t i = 1; i <= 8u; ++i)
+						v[i - 1] = i < nw ? __ldcg(words + base + q + i) : 0u;
+#pragma unroll
+					for (uint32_t i = 1; i <= 8u; ++i)
+						hit = hit && (i >= nw || v[i - 1] == me[i]);
+				}
 				const uint32_t m = __ballot_sync(full, hit);
 				if (m && found == kNull)
 					found = base + off + k * 32u + __ffs(m) - 1u;

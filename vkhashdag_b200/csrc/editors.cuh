@@ -161,6 +161,45 @@ __device__ inline bool voxel_in_range(const hd_edit_desc &d, uint32_t x, uint32_
 	return false;
 }
 
+// Terrain fill of one 4x4x4 leaf, warp-cooperative (all 32 lanes call it with the same edit and leaf origin).
+// A leaf's 4x4 footprint lies inside ONE lattice cell of every octave whose cell is >= 4 voxels wide, so the four
+// lattice corners of each octave are hashed once per warp (lane 4*o + k hashes corner k of octave o) and handed round
+// with shuffles; lane l < 16 then interpolates the height of column (x = l & 3, z = l >> 2) and the voxel owners read
+// it with one more shuffle: 16 height evaluations per leaf instead of 64, and ~1/4 of the hashing in each.
+// The integer arithmetic is terrain_height's, value for value.  Returns false when the octave layout does not fit
+// (more than 8 octaves or a cell narrower than a leaf); the caller then evaluates per voxel.
+__device__ __forceinline__ bool terrain_leaf_pair(const hd_edit_desc &d, uint32_t ox, uint32_t oz, uint32_t vx, uint32_t vy,
+                                                  uint32_t vz, bool &in_a, bool &in_b) {
+	const uint32_t lane = threadIdx.x & 31u, full = 0xFFFFFFFFu;
+	uint32_t n_oct = 0;
+	TerrainOctave oc;
+	bool fits = true;
+	for (; terrain_octave(d, n_oct, oc); ++n_oct)
+		fits = fits && oc.cell_bits >= 2u;
+	if (!fits || n_oct > 8u)
+		return false;
+	uint32_t lat = 0;
+	if (terrain_octave(d, lane >> 2, oc))
+		lat = terrain_lattice(oc.hseed, (ox >> oc.cell_bits) + (lane & 1u), (oz >> oc.cell_bits) + ((lane >> 1) & 1u));
+	const uint32_t cx = ox + (lane & 3u), cz = oz + ((lane >> 2) & 3u); // this lane's column (lanes 16..31 repeat 0..15)
+	uint32_t h = d.p0[0];
+	for (uint32_t o = 0; o < n_oct; ++o) {
+		const uint32_t v00 = __shfl_sync(full, lat, 4u * o), v10 = __shfl_sync(full, lat, 4u * o + 1u),
+		               v01 = __shfl_sync(full, lat, 4u * o + 2u), v11 = __shfl_sync(full, lat, 4u * o + 3u);
+		const uint32_t c = d.p0[1] - 2u * o, m = (1u << c) - 1u;
+		const uint32_t r = terrain_bilerp(v00, v10, v01, v11, cx & m, cz & m, c);
+		h += uint32_t((uint64_t(r) * (d.p1[0] >> (2u * o))) >> 16);
+	}
+	const uint32_t col = ((vz & 3u) << 2) | (vx & 3u);
+	const uint32_t ha = __shfl_sync(full, h, col), hb = __shfl_sync(full, h, col + 8u); // voxel b: z + 2
+	bool inside = true;
+	if (d.p1[1] != 0u)
+		inside = (vx >> d.p1[1]) == 0u && (vz >> d.p1[1]) == 0u; // z + 2 stays inside the same 4-aligned leaf
+	in_a = inside && vy < ha;
+	in_b = inside && vy < hb;
+	return true;
+}
+
 // EditVoxel (main.cpp:60-63,133-142)
 __device__ __forceinline__ bool edit_voxel(const hd_edit_desc &d, uint32_t x, uint32_t y, uint32_t z, bool voxel) {
 	const bool in = voxel_in_range(d, x, y, z);
