@@ -162,13 +162,14 @@ struct Filtered {
 __device__ __forceinline__ bool is_noop(uint32_t kind, uint32_t cur, uint32_t filled_ptr) {
 	return kind == HD_EDIT_SPHERE_DIG ? cur == kNull : cur == filled_ptr;
 }
+template <bool kTerrain>
 __device__ inline Filtered filter_list(const hd_edit_desc *__restrict__ edits, const uint32_t *__restrict__ list,
                                        uint32_t len, uint32_t bits, uint32_t x, uint32_t y, uint32_t z, uint32_t cur,
                                        uint32_t filled_ptr) {
 	Filtered f{cur, 0u, 0u, 0u};
 	int j = int(len) - 1;
 	for (; j >= 0; --j) {
-		const EditType t = edit_node(edits[list[j]], bits, x, y, z);
+		const EditType t = edit_node<kTerrain>(edits[list[j]], bits, x, y, z);
 		if (t == kFill) {
 			f.cur = filled_ptr;
 			break;
@@ -198,7 +199,7 @@ __device__ inline Filtered filter_list(const hd_edit_desc *__restrict__ edits, c
 		} else {
 			while (f.count) {
 				const hd_edit_desc &e = edits[list[f.start]];
-				const bool proceed = edit_node(e, bits, x, y, z) == kProceed;
+				const bool proceed = edit_node<kTerrain>(e, bits, x, y, z) == kProceed;
 				if (proceed && !is_noop(e.kind, f.cur, filled_ptr))
 					break;
 				if (proceed)
@@ -209,6 +210,7 @@ __device__ inline Filtered filter_list(const hd_edit_desc *__restrict__ edits, c
 	}
 	return f;
 }
+template <bool kTerrain>
 __device__ inline void write_list(const hd_edit_desc *__restrict__ edits, const uint32_t *__restrict__ list, uint32_t len,
                                   uint32_t bits, uint32_t x, uint32_t y, uint32_t z, const Filtered &f, uint32_t *dst) {
 	if (len <= 32) {
@@ -220,7 +222,7 @@ __device__ inline void write_list(const hd_edit_desc *__restrict__ edits, const 
 		}
 	} else {
 		for (uint32_t j = f.start; j < len; ++j)
-			if (edit_node(edits[list[j]], bits, x, y, z) == kProceed)
+			if (edit_node<kTerrain>(edits[list[j]], bits, x, y, z) == kProceed)
 				*dst++ = list[j];
 	}
 }
@@ -407,6 +409,7 @@ __global__ void __launch_bounds__(kBlock) k_down_long(Geometry g, uint32_t level
 // grid from a known item count, a grid-stride loop over the device-resident count on the low-latency path).
 // (tid0, nthreads) = this thread's index among, and the number of, the threads that share the level: the whole grid, or
 // one CTA when the fused kernel walks a small level alone.
+template <bool kTerrain>
 __device__ __forceinline__ void phase_down(const Geometry &g, uint32_t level /* of `in` */,
                                            const uint32_t *__restrict__ words, const hd_edit_desc *__restrict__ edits,
                                            const uint32_t *__restrict__ filled, const LevelView &in, const LevelView &out,
@@ -433,7 +436,7 @@ __device__ __forceinline__ void phase_down(const Geometry &g, uint32_t level /* 
 			list = in.lists + in.list_off[item];
 			len = in.list_len[item];
 			if (len <= 32u)
-				f = filter_list(edits, list, len, bits, x, y, z, child, filled[level + 1u]);
+				f = filter_list<kTerrain>(edits, list, len, bits, x, y, z, child, filled[level + 1u]);
 		}
 		uint32_t slot, entry_off;
 		const bool made = alloc_item(ctr, items_ctr, entries_ctr, valid && f.count != 0, f.count, out.cap, out.cap_entries,
@@ -446,26 +449,30 @@ __device__ __forceinline__ void phase_down(const Geometry &g, uint32_t level /* 
 			out.parent[slot] = (item << 3) | c;
 			out.list_off[slot] = entry_off;
 			out.list_len[slot] = f.count;
-			write_list(edits, list, len, bits, x, y, z, f, out.lists + entry_off);
+			write_list<kTerrain>(edits, list, len, bits, x, y, z, f, out.lists + entry_off);
 			in.child_new[size_t(item) * 8u + c] = kPending;
 		} else {
 			in.child_new[size_t(item) * 8u + c] = f.cur;
 		}
 	}
 }
+template <bool kTerrain>
 __global__ void __launch_bounds__(kBlock) k_down(Geometry g, uint32_t level, const uint32_t *__restrict__ words,
                                                  const hd_edit_desc *__restrict__ edits,
                                                  const uint32_t *__restrict__ filled, LevelView in, LevelView out,
                                                  DevCounters *ctr, uint32_t *items_ctr, uint32_t *entries_ctr) {
-	phase_down(g, level, words, edits, filled, in, out, ctr, items_ctr, entries_ctr, blockIdx.x * blockDim.x + threadIdx.x,
+	phase_down<kTerrain>(g, level, words, edits, filled, in, out, ctr, items_ctr, entries_ctr, blockIdx.x * blockDim.x + threadIdx.x,
 	           gridDim.x * blockDim.x);
 }
 
 // Leaf pass: one warp per 4x4x4 leaf (a persistent grid-stride variant measured 10-20 % slower: the per-leaf work is
 // short and uniform, so the hardware CTA scheduler balances it better); lane l owns voxels l and l+32 (NodeCoord::GetLeafCoord, NodeCoord.hpp:32-43).
-__global__ void __launch_bounds__(kBlock) k_leaf(Geometry g, const uint32_t *__restrict__ words,
-                                                 const hd_edit_desc *__restrict__ edits, LevelView lv,
-                                                 DevCounters *ctr) {
+// kTerrain = false: the batch holds no terrain edit — the generator is compiled out and the kernel fits 32 registers
+// (8 CTAs of 256 threads per SM; the pass is latency-bound on its list -> descriptor loads, so resident warps matter).
+template <bool kTerrain>
+__global__ void __launch_bounds__(kBlock, kTerrain ? 5 : 8) k_leaf(Geometry g, const uint32_t *__restrict__ words,
+                                                                    const hd_edit_desc *__restrict__ edits, LevelView lv,
+                                                                    DevCounters *ctr) {
 	const uint32_t lane = threadIdx.x & 31u, n = lv.count();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n; item += warps) {
@@ -486,12 +493,11 @@ __global__ void __launch_bounds__(kBlock) k_leaf(Geometry g, const uint32_t *__r
 		for (uint32_t j = 0; j < len; ++j) {
 			const hd_edit_desc &e = edits[list[j]];
 			bool ia, ib;
-			if (e.kind == HD_EDIT_TERRAIN_FILL && terrain_leaf_pair(e, x << 2, z << 2, vx, vy, vz, ia, ib)) { // warp-uniform
+			if (kTerrain && e.kind == HD_EDIT_TERRAIN_FILL && terrain_leaf_pair(e, x << 2, z << 2, vx, vy, vz, ia, ib)) { // warp-uniform
 				a = a || ia, b = b || ib;
 				continue;
 			}
-			a = edit_voxel(e, vx, vy, vz, a);
-			b = edit_voxel(e, vx, vy, vz + 2u, b);
+			edit_voxel_pair<kTerrain>(e, vx, vy, vz, a, b);
 		}
 		const uint32_t n0 = __ballot_sync(0xFFFFFFFFu, a), n1 = __ballot_sync(0xFFFFFFFFu, b);
 		if (lane == 0) {
@@ -898,8 +904,7 @@ __device__ __forceinline__ void phase_up(const Geometry &g, uint32_t level, bool
 			bool a = w0 >> lane & 1u, b = w1 >> lane & 1u;
 			for (uint32_t j = 0; j < len; ++j) {
 				const hd_edit_desc &e = edits[list[j]];
-				a = edit_voxel(e, vx, vy, vz, a);
-				b = edit_voxel(e, vx, vy, vz + 2u, b);
+				edit_voxel_pair<false>(e, vx, vy, vz, a, b);
 			}
 			const uint32_t n0 = __ballot_sync(full, a), n1 = __ballot_sync(full, b);
 			if (n0 != w0 || n1 != w1) {
@@ -1008,8 +1013,8 @@ __global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_const
 		__syncthreads();
 		uint32_t l = 0;
 		for (; l + 1 < L && items[l] <= kSoloDown; ++l) {
-			phase_down(g, l, a.words, edits, a.filled, a.lv[l], a.lv[l + 1], ctr, &ctr->lvl_items[l + 1], &ctr->lvl_entries[l + 1],
-			           threadIdx.x, blockDim.x);
+			phase_down<false>(g, l, a.words, edits, a.filled, a.lv[l], a.lv[l + 1], ctr, &ctr->lvl_items[l + 1],
+			                  &ctr->lvl_entries[l + 1], threadIdx.x, blockDim.x);
 			__syncthreads();
 		}
 		if (threadIdx.x == 0)
@@ -1018,8 +1023,8 @@ __global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_const
 	grid.sync();
 	// ---- stage B (grid): the remaining top-down levels ----
 	for (uint32_t l = *(volatile uint32_t *)&ctr->next_items; l + 1 < L; ++l) {
-		phase_down(g, l, a.words, edits, a.filled, a.lv[l], a.lv[l + 1], ctr, &ctr->lvl_items[l + 1], &ctr->lvl_entries[l + 1], gtid,
-		           gthreads);
+		phase_down<false>(g, l, a.words, edits, a.filled, a.lv[l], a.lv[l + 1], ctr, &ctr->lvl_items[l + 1], &ctr->lvl_entries[l + 1],
+		                  gtid, gthreads);
 		grid.sync();
 	}
 	// ---- stage C (grid): bottom-up over the levels that are worth the grid; then CTA 0 finishes the small top ----
@@ -1474,6 +1479,9 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 	HD_LAUNCH_CHECK();
 	HD_CUDA_TRY(cudaMemsetAsync(s->ctr, 0, sizeof(DevCounters), st));
 
+	bool terrain = false; // kernels for batches without a terrain edit have the generator compiled out
+	for (uint32_t i = 0; i < n_edits && !terrain; ++i)
+		terrain = edits_host[i].kind == HD_EDIT_TERRAIN_FILL;
 	levels.resize(L);
 	HD_CUDA_TRY(levels[0].init(1, n_edits, L == 1, st));
 	k_root<<<1, 32, 0, st>>>(g, edits_dev, n_edits, iota, s->filled_dev, root_in, levels[0].v, s->ctr, nullptr);
@@ -1505,8 +1513,12 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 		HD_CUDA_TRY(out.init(uint32_t(cap), uint32_t(cap_e), l + 2 == L, st));
 		// reset per-level cursors (stats keep accumulating)
 		HD_CUDA_TRY(cudaMemsetAsync(&s->ctr->next_items, 0, 3 * sizeof(uint32_t), st));
-		k_down<<<grid_for(uint64_t(in.v.n) * 8), kBlock, 0, st>>>(g, l, p->words, edits_dev, s->filled_dev, in.v, out.v,
-		                                                          s->ctr, &s->ctr->next_items, &s->ctr->next_entries);
+		if (terrain)
+			k_down<true><<<grid_for(uint64_t(in.v.n) * 8), kBlock, 0, st>>>(g, l, p->words, edits_dev, s->filled_dev, in.v, out.v,
+			                                                                s->ctr, &s->ctr->next_items, &s->ctr->next_entries);
+		else
+			k_down<false><<<grid_for(uint64_t(in.v.n) * 8), kBlock, 0, st>>>(g, l, p->words, edits_dev, s->filled_dev, in.v, out.v,
+			                                                                 s->ctr, &s->ctr->next_items, &s->ctr->next_entries);
 		HD_LAUNCH_CHECK();
 		if (long_lists) {
 			k_down_long<<<grid_for(uint64_t(in.v.n) * 8 * 32), kBlock, 0, st>>>(g, l, p->words, edits_dev, s->filled_dev,
@@ -1531,7 +1543,10 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 	if (deepest == L - 1) {
 		LevelAlloc &lv = levels[L - 1];
 		HD_CUDA_TRY(lv.init_up(true));
-		k_leaf<<<grid_for(uint64_t(lv.v.n) * 32), kBlock, 0, st>>>(g, p->words, edits_dev, lv.v, s->ctr);
+		if (terrain)
+			k_leaf<true><<<grid_for(uint64_t(lv.v.n) * 32), kBlock, 0, st>>>(g, p->words, edits_dev, lv.v, s->ctr);
+		else
+			k_leaf<false><<<grid_for(uint64_t(lv.v.n) * 32), kBlock, 0, st>>>(g, p->words, edits_dev, lv.v, s->ctr);
 		HD_LAUNCH_CHECK();
 		rs = run_upsert(p, L - 1, lv.v.n, 2, lv.v.cand, lv.v.state, lv.v.winner, lv.v.cur, lv.v.result);
 		if (rs != HD_OK)
@@ -1593,7 +1608,7 @@ static hd_status fast_enqueue(hd_pool *p) {
 	k_root<<<1, 32, 0, st>>>(g, f.dyn_dev->edits, 0, f.iota_dev, s->filled_dev, 0, f.lv[0], s->ctr, &f.dyn_dev->root);
 	HD_LAUNCH_CHECK();
 	for (uint32_t l = 0; l + 1 < L; ++l) {
-		k_down<<<fast_grid(p, uint64_t(f.lv[l].cap) * 8), kBlock, 0, st>>>(g, l, p->words, f.dyn_dev->edits, s->filled_dev, f.lv[l],
+		k_down<false><<<fast_grid(p, uint64_t(f.lv[l].cap) * 8), kBlock, 0, st>>>(g, l, p->words, f.dyn_dev->edits, s->filled_dev, f.lv[l],
 		                                                                 f.lv[l + 1], s->ctr, &s->ctr->lvl_items[l + 1],
 		                                                                 &s->ctr->lvl_entries[l + 1]);
 		HD_LAUNCH_CHECK();

@@ -92,6 +92,7 @@ __device__ inline void terrain_bounds(const hd_edit_desc &d, uint32_t lx, uint32
 }
 
 // EditNode: node at `level` with integer position (x,y,z); bits = voxel_level - level.
+template <bool kTerrain = true>
 __device__ inline EditType edit_node(const hd_edit_desc &d, uint32_t bits, uint32_t x, uint32_t y, uint32_t z) {
 	const uint32_t lb[3] = {x << bits, y << bits, z << bits};
 	const uint32_t ub[3] = {(x + 1u) << bits, (y + 1u) << bits, (z + 1u) << bits};
@@ -107,6 +108,27 @@ __device__ inline EditType edit_node(const hd_edit_desc &d, uint32_t bits, uint3
 	}
 	case HD_EDIT_SPHERE_FILL:
 	case HD_EDIT_SPHERE_DIG: { // main.cpp:77-106
+		// near the sphere (every |lo|, |hi| < 37 837) the sums stay below 2^32 and 32-bit arithmetic gives the same values
+		const int32_t l0 = int32_t(lb[0] - d.p0[0]), l1 = int32_t(lb[1] - d.p0[1]), l2 = int32_t(lb[2] - d.p0[2]);
+		const int32_t h0 = int32_t(ub[0] - d.p0[0]), h1 = int32_t(ub[1] - d.p0[1]), h2 = int32_t(ub[2] - d.p0[2]);
+		const uint32_t far = max(max(max(uint32_t(abs(l0)), uint32_t(abs(h0))), max(uint32_t(abs(l1)), uint32_t(abs(h1)))),
+		                         max(uint32_t(abs(l2)), uint32_t(abs(h2))));
+		if (far < 37837u && bits < 22u) {
+			const int32_t lo[3] = {l0, l1, l2}, hi[3] = {h0, h1, h2};
+			uint32_t mx = 0, mn = 0;
+#pragma unroll
+			for (int i = 0; i < 3; ++i) {
+				const uint32_t lo2 = uint32_t(lo[i] * lo[i]), hi2 = uint32_t(hi[i] * hi[i]);
+				mx += lo2 > hi2 ? lo2 : hi2;
+				if (lo[i] > 0)
+					mn += lo2;
+				if (hi[i] < 0)
+					mn += hi2;
+			}
+			if (uint64_t(mx) <= d.r2)
+				return d.kind == HD_EDIT_SPHERE_DIG ? kClear : kFill;
+			return uint64_t(mn) > d.r2 ? kNotAffected : kProceed;
+		}
 		uint64_t max_n2 = 0, min_n2 = 0;
 #pragma unroll
 		for (int i = 0; i < 3; ++i) {
@@ -123,6 +145,8 @@ __device__ inline EditType edit_node(const hd_edit_desc &d, uint32_t bits, uint3
 		return min_n2 > d.r2 ? kNotAffected : kProceed;
 	}
 	case HD_EDIT_TERRAIN_FILL: {
+		if (!kTerrain)
+			return kNotAffected;
 		bool whole = true; // footprint fully inside the terrain patch (p1[1] = extent bits, 0 = whole world)
 		if (d.p1[1] != 0u) {
 			const uint64_t e = 1ull << d.p1[1], s = 1ull << bits;
@@ -142,7 +166,9 @@ __device__ inline EditType edit_node(const hd_edit_desc &d, uint32_t bits, uint3
 	return kNotAffected;
 }
 
-// VoxelInRange (main.cpp:57-59,127-132)
+// VoxelInRange (main.cpp:57-59,127-132).  kTerrain = false compiles the terrain generator out (kernels launched for
+// batches without a terrain edit: fewer registers, more resident warps).
+template <bool kTerrain = true>
 __device__ inline bool voxel_in_range(const hd_edit_desc &d, uint32_t x, uint32_t y, uint32_t z) {
 	switch (d.kind) {
 	case HD_EDIT_AABB_FILL:
@@ -154,11 +180,32 @@ __device__ inline bool voxel_in_range(const hd_edit_desc &d, uint32_t x, uint32_
 		return uint64_t(dx * dx + dy * dy + dz * dz) <= d.r2;
 	}
 	case HD_EDIT_TERRAIN_FILL:
+		if (!kTerrain)
+			return false;
 		if (d.p1[1] != 0u && ((x >> d.p1[1]) != 0u || (z >> d.p1[1]) != 0u))
 			return false;
 		return y < terrain_height(d, x, z);
 	}
 	return false;
+}
+
+// Sphere VoxelInRange for the two voxels a lane owns in a leaf, (x, y, z) and (x, y, z + 2).  The reference compares
+// dx^2 + dy^2 + dz^2 <= r2 in 64 bits (main.cpp:127-132); when every |d| < 37 837 the sum is below 2^32 and 32-bit
+// arithmetic gives the same value (3 * 37 836^2 = 4 294 688 688 < 2^32) — always the case next to the sphere's surface
+// for r < 37 000, i.e. at every leaf a brush reaches.  Larger distances take the 64-bit form.
+__device__ __forceinline__ void sphere_in_range_pair(const hd_edit_desc &d, uint32_t x, uint32_t y, uint32_t z, bool &in_a,
+                                                     bool &in_b) {
+	const int32_t dx = int32_t(x - d.p0[0]), dy = int32_t(y - d.p0[1]), dz = int32_t(z - d.p0[2]); // world <= 2^22: no wrap
+	const uint32_t ax = uint32_t(dx < 0 ? -dx : dx), ay = uint32_t(dy < 0 ? -dy : dy), az = uint32_t(dz < 0 ? -dz : dz) + 2u;
+	if (max(ax, max(ay, az)) < 37837u) {
+		const uint32_t s = uint32_t(dx * dx) + uint32_t(dy * dy);
+		const uint32_t na = s + uint32_t(dz * dz), nb = s + uint32_t((dz + 2) * (dz + 2));
+		in_a = uint64_t(na) <= d.r2, in_b = uint64_t(nb) <= d.r2;
+	} else {
+		const long long X = dx, Y = dy, Z = dz;
+		const uint64_t s = uint64_t(X * X + Y * Y);
+		in_a = s + uint64_t(Z * Z) <= d.r2, in_b = s + uint64_t((Z + 2) * (Z + 2)) <= d.r2;
+	}
 }
 
 // Terrain fill of one 4x4x4 leaf, warp-cooperative (all 32 lanes call it with the same edit and leaf origin).
@@ -201,9 +248,24 @@ __device__ __forceinline__ bool terrain_leaf_pair(const hd_edit_desc &d, uint32_
 }
 
 // EditVoxel (main.cpp:60-63,133-142)
+template <bool kTerrain = true>
 __device__ __forceinline__ bool edit_voxel(const hd_edit_desc &d, uint32_t x, uint32_t y, uint32_t z, bool voxel) {
-	const bool in = voxel_in_range(d, x, y, z);
+	const bool in = voxel_in_range<kTerrain>(d, x, y, z);
 	return d.kind == HD_EDIT_SPHERE_DIG ? (voxel && !in) : (voxel || in);
+}
+// EditVoxel for the lane's two voxels (z and z + 2) of a leaf; spheres share dx^2 + dy^2 between them.
+template <bool kTerrain>
+__device__ __forceinline__ void edit_voxel_pair(const hd_edit_desc &d, uint32_t x, uint32_t y, uint32_t z, bool &a, bool &b) {
+	const uint32_t kind = d.kind;
+	if (kind == HD_EDIT_SPHERE_FILL || kind == HD_EDIT_SPHERE_DIG) {
+		bool ia, ib;
+		sphere_in_range_pair(d, x, y, z, ia, ib);
+		a = kind == HD_EDIT_SPHERE_DIG ? (a && !ia) : (a || ia);
+		b = kind == HD_EDIT_SPHERE_DIG ? (b && !ib) : (b || ib);
+	} else {
+		a = edit_voxel<kTerrain>(d, x, y, z, a);
+		b = edit_voxel<kTerrain>(d, x, y, z + 2u, b);
+	}
 }
 
 } // namespace hd
