@@ -114,8 +114,13 @@ typedef struct hd_trace_outputs {
 	                          requesting it selects an instrumented kernel variant — not for timed runs */
 } hd_trace_outputs;
 
-/* Screen-tile sharding of one frame over `world` GPUs: tile t = ty*tiles_x+tx (tile_w x tile_h px)
- * belongs to rank t % world; a rank's outputs are tile-major: index = (t/world)*tile_w*tile_h + ly*tile_w + lx. */
+/* Screen-tile sharding of one frame over `world` GPUs (tiles of tile_w x tile_h px, tiles_x per row).
+ * Ownership interleaves the ranks in BOTH directions so that cheap (sky) and expensive (silhouette) regions spread evenly:
+ *   tiles_x % world != 0:  tile t = ty*tiles_x + tx belongs to rank t % world, local index t / world (row-major round
+ *                          robin; the row length already shifts the pattern from row to row);
+ *   tiles_x % world == 0:  tile (tx, ty) belongs to rank (tx + ty) % world, local index ty*(tiles_x/world) + tx/world
+ *                          (plain round robin would give every rank the same columns in every row).
+ * A rank's outputs are tile-major: index = local*tile_w*tile_h + ly*tile_w + lx.  hd_tile_shard_locate inverts the map. */
 typedef struct hd_tile_shard {
 	uint32_t tile_w, tile_h;
 	uint32_t rank, world;
@@ -233,6 +238,9 @@ hd_status hd_trace_submit(hd_pool *pool, const hd_trace_params *params, const hd
 hd_status hd_trace_collect(hd_pool *pool, uint32_t slot);
 /* pixels a rank owns under a shard (size of its output planes) */
 uint64_t hd_tile_shard_pixels(const hd_trace_params *params, const hd_tile_shard *shard);
+/* Tile coordinates of the rank's `local`-th tile (host-only helper for stitching / display); HD_ERR_INVALID past the end. */
+hd_status hd_tile_shard_locate(const hd_trace_params *params, const hd_tile_shard *shard, uint32_t local, uint32_t *tile_x,
+                               uint32_t *tile_y);
 /* single pick ray: NodePoolTraversal::Traversal<float> (NodePoolTraversal.hpp:93-256), main.cpp:320-321.
  * Returns hit flag in *out_hit and the float hit position in out_pos[3]. */
 hd_status hd_traverse_ray(hd_pool *pool, uint32_t root, const float o[3], const float d[3], int *out_hit,

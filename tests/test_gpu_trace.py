@@ -67,28 +67,27 @@ def test_trace_tile_shards_cover_frame(oracle, hd):
     cfg, opool, root = build_scene(oracle, level_count=9)
     dev = hd.DAGNodePool(cfg)
     dev.UploadFrom(opool)
-    W, H, tw, th = 400, 250, 64, 64
-    P = abi.camera_params(cfg, root, (0.5, 0.6, 1.3), np.pi, -0.2, W, H)
-    full = dev.Trace(P)
-    tiles_x, tiles_y = -(-W // tw), -(-H // th)
-    for world in (1, 2, 3, 8):
-        seen = np.zeros((H, W), bool)
-        for rank in range(world):
-            part = dev.Trace(P, shard=(tw, th, rank, world))
-            n_local = len(range(rank, tiles_x * tiles_y, world))
-            assert part["rgba8"].size == n_local * tw * th
-            for lt in range(n_local):
-                t = lt * world + rank
-                tx, ty = t % tiles_x, t // tiles_x
-                x0, y0 = tx * tw, ty * th
-                w, h = min(tw, W - x0), min(th, H - y0)
-                for name in ("rgba8", "iters"):
-                    blk = part[name][lt * tw * th:(lt + 1) * tw * th].reshape(th, tw)[:h, :w]
-                    assert np.array_equal(blk, full[name][y0:y0 + h, x0:x0 + w])
-                blk = part["hits"][lt * tw * th:(lt + 1) * tw * th].reshape(th, tw)[:h, :w]
-                assert np.array_equal(blk, full["hits"][y0:y0 + h, x0:x0 + w])
-                seen[y0:y0 + h, x0:x0 + w] = True
-        assert seen.all()
+    from vkhashdag_b200 import replica
+    tw, th = 64, 64
+    # 400 px: 7 tiles per row (row-major round robin); 512 px: 8 per row (the (tx + ty) % world map for world 2, 4, 8)
+    for W, H, worlds in ((400, 250, (1, 2, 3, 8)), (512, 200, (2, 3, 4, 8))):
+        P = abi.camera_params(cfg, root, (0.5, 0.6, 1.3), np.pi, -0.2, W, H)
+        full = dev.Trace(P)
+        for world in worlds:
+            seen = np.zeros((H, W), bool)
+            for rank in range(world):
+                part = dev.Trace(P, shard=(tw, th, rank, world))
+                tiles = replica.local_tiles(W, H, tw, th, rank, world)
+                assert part["rgba8"].size == len(tiles) * tw * th
+                for lt, tx, ty in tiles:
+                    assert not seen[ty * th, tx * tw]   # no tile is owned twice
+                    x0, y0 = tx * tw, ty * th
+                    w, h = min(tw, W - x0), min(th, H - y0)
+                    for name in ("rgba8", "iters", "hits"):
+                        blk = part[name][lt * tw * th:(lt + 1) * tw * th].reshape(th, tw)[:h, :w]
+                        assert np.array_equal(blk, full[name][y0:y0 + h, x0:x0 + w])
+                    seen[y0:y0 + h, x0:x0 + w] = True
+            assert seen.all()
     dev.close()
 
 

@@ -144,9 +144,20 @@ def test_tile_partition_matches_c_abi():
             owned = set()
             for rank in range(world):
                 tiles = replica.local_tiles(W, H, 64, 64, rank, world)
-                assert len(tiles) * 64 * 64 == L.hd_tile_shard_pixels(C.byref(P), C.byref(api.HdTileShard(64, 64, rank, world)))
-                owned |= {(tx, ty) for _, tx, ty in tiles}
+                shard = api.HdTileShard(64, 64, rank, world)
+                assert len(tiles) * 64 * 64 == L.hd_tile_shard_pixels(C.byref(P), C.byref(shard))
+                tx, ty = C.c_uint32(), C.c_uint32()
+                for lt, ex, ey in tiles:    # same map as the kernel's (hd_tile_shard_locate shares tile_of with it)
+                    assert L.hd_tile_shard_locate(C.byref(P), C.byref(shard), lt, C.byref(tx), C.byref(ty)) == 0
+                    assert (tx.value, ty.value) == (ex, ey)
+                    assert replica.tile_owner(ex, ey, -(-W // 64), world) == rank
+                assert L.hd_tile_shard_locate(C.byref(P), C.byref(shard), len(tiles), C.byref(tx), C.byref(ty)) != 0
+                assert not owned & {(x, y) for _, x, y in tiles}
+                owned |= {(x, y) for _, x, y in tiles}
             assert len(owned) == (-(-W // 64)) * (-(-H // 64))
+    # a row holding a whole number of rounds must not give a rank the same columns in every row
+    cols = {tx for _, tx, ty in replica.local_tiles(7680, 4320, 64, 64, 0, 8)}
+    assert len(cols) == 120
 
 
 def test_bench_frame_dims_weak_scaling():

@@ -64,6 +64,7 @@ SYMBOLS = [
     "hd_pool_load", "hd_gc", "hd_trace_submit", "hd_trace_collect", "hd_beam_dev",
     "hd_trace_with_beam_dev", "hd_trace_with_beam", "hd_color_config", "hd_color_root", "hd_color_leaf_level",
     "hd_color_sizes", "hd_color_read", "hd_edit_color", "hd_edit_last_path",
+    "hd_tile_shard_locate",
 ]
 
 
@@ -126,6 +127,7 @@ def lib():
     L.hd_trace_collect.argtypes = [vp, u32]
     L.hd_tile_shard_pixels.restype = u64
     L.hd_tile_shard_pixels.argtypes = [C.POINTER(HdTraceParams), C.POINTER(HdTileShard)]
+    L.hd_tile_shard_locate.argtypes = [C.POINTER(HdTraceParams), C.POINTER(HdTileShard), u32, pu32, pu32]
     L.hd_traverse_ray.argtypes = [vp, u32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(ci),
                                   C.POINTER(C.c_float)]
     L.hd_dirty_count.argtypes = [vp, pu32, C.POINTER(u64)]

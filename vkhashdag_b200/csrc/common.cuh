@@ -57,6 +57,19 @@ struct Geometry {
 
 bool make_geometry(const hd_config &cfg, Geometry &g);
 
+// hd_tile_shard ownership map (include/hashdag_b200.h): the rank's `local`-th tile -> tile coordinates
+__host__ __device__ __forceinline__ void tile_of(uint32_t local, uint32_t rank, uint32_t world, uint32_t tiles_x, uint32_t &tx,
+                                                 uint32_t &ty) {
+	if (tiles_x % world != 0u) {
+		const uint32_t t = local * world + rank;
+		tx = t % tiles_x, ty = t / tiles_x;
+	} else {
+		const uint32_t per_row = tiles_x / world;
+		ty = local / per_row;
+		tx = (local % per_row) * world + (rank + world - ty % world) % world;
+	}
+}
+
 struct EditScratch; // edit.cu
 
 } // namespace hd

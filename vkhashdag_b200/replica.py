@@ -11,15 +11,19 @@ host-memory stand-in for the pool).
 import torch
 
 
-def tile_owner(tile_index, world):
-    """Rank that owns screen tile t (hd_tile_shard: round-robin in row-major tile order)."""
-    return tile_index % world
+def tile_owner(tx, ty, tiles_x, world):
+    """Rank that owns screen tile (tx, ty) — the hd_tile_shard map of include/hashdag_b200.h: row-major round robin,
+    or (tx + ty) % world when a row holds a whole number of rounds (so that ranks do not end up with fixed columns)."""
+    return (ty * tiles_x + tx) % world if tiles_x % world else (tx + ty) % world
 
 
 def local_tiles(width, height, tile_w, tile_h, rank, world):
     """[(local_index, tile_x, tile_y)] of the tiles a rank owns, in its output order."""
     tiles_x, tiles_y = -(-width // tile_w), -(-height // tile_h)
-    return [(lt, t % tiles_x, t // tiles_x) for lt, t in enumerate(range(rank, tiles_x * tiles_y, world))]
+    if tiles_x % world:
+        return [(lt, t % tiles_x, t // tiles_x) for lt, t in enumerate(range(rank, tiles_x * tiles_y, world))]
+    per_row = tiles_x // world
+    return [(ty * per_row + k, k * world + (rank - ty) % world, ty) for ty in range(tiles_y) for k in range(per_row)]
 
 
 def assemble_frame(parts, width, height, tile_w, tile_h, world, dtype=None):
