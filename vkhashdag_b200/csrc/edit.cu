@@ -470,49 +470,61 @@ __global__ void __launch_bounds__(kBlock) k_down(Geometry g, uint32_t level, con
 // kTerrain = false: the batch holds no terrain edit — the generator is compiled out and the kernel fits 32 registers
 // (8 CTAs of 256 threads per SM; the pass is latency-bound on its list -> descriptor loads, so resident warps matter).
 template <bool kTerrain>
-__global__ void __launch_bounds__(kBlock, kTerrain ? 5 : 8) k_leaf(Geometry g, const uint32_t *__restrict__ words,
+__global__ void __launch_bounds__(kBlock, kTerrain ? 4 : 6) k_leaf(Geometry g, const uint32_t *__restrict__ words,
                                                                     const hd_edit_desc *__restrict__ edits, LevelView lv,
                                                                     DevCounters *ctr) {
-	const uint32_t lane = threadIdx.x & 31u, n = lv.count();
+	// A warp takes 32 consecutive items at a time: lane i fetches item i's queue record and old leaf (coalesced loads, 32
+	// independent leaf gathers in flight), then the warp walks the 32 leaves one after the other with the record handed
+	// round by shuffles, and lane i writes item i's result back (coalesced again).  One-warp-per-item loads cost a 32-byte
+	// sector per 4-byte field; this way the per-leaf loads are the edit list and its descriptors only.
+	const uint32_t lane = threadIdx.x & 31u, full = 0xFFFFFFFFu, n = lv.count();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-	for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n; item += warps) {
-		const uint32_t cur = lv.cur[item];
-		const uint32_t *list = lv.lists + lv.list_off[item];
-		const uint32_t len = lv.list_len[item];
-		uint32_t x, y, z;
-		unpack_pos(lv.pos[item], x, y, z);
-		uint32_t w0 = 0, w1 = 0;
-		if (cur != kNull) {
-			const uint2 w = *reinterpret_cast<const uint2 *>(words + cur);
-			w0 = w.x, w1 = w.y;
-		}
-		const uint32_t vx = (x << 2) | ((lane >> 2) & 2u) | (lane & 1u);
-		const uint32_t vy = (y << 2) | ((lane >> 3) & 2u) | ((lane >> 1) & 1u);
-		const uint32_t vz = (z << 2) | ((lane >> 2) & 1u); // voxel l: z1 = 0; voxel l+32: z1 = 1 (adds 2)
-		bool a = w0 >> lane & 1u, b = w1 >> lane & 1u;
-		for (uint32_t j = 0; j < len; ++j) {
-			const hd_edit_desc &e = edits[list[j]];
-			bool ia, ib;
-			if (kTerrain && e.kind == HD_EDIT_TERRAIN_FILL && terrain_leaf_pair(e, x << 2, z << 2, vx, vy, vz, ia, ib)) { // warp-uniform
-				a = a || ia, b = b || ib;
-				continue;
+	for (uint32_t base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; base < n; base += warps * 32u) {
+		const uint32_t mine = base + lane;
+		uint32_t m_cur = kNull, m_off = 0, m_len = 0, m_w0 = 0, m_w1 = 0;
+		uint64_t m_pos = 0;
+		if (mine < n) {
+			m_cur = lv.cur[mine], m_off = lv.list_off[mine], m_len = lv.list_len[mine], m_pos = lv.pos[mine];
+			if (m_cur != kNull) {
+				const uint2 w = *reinterpret_cast<const uint2 *>(words + m_cur);
+				m_w0 = w.x, m_w1 = w.y;
 			}
-			edit_voxel_pair<kTerrain>(e, vx, vy, vz, a, b);
 		}
-		const uint32_t n0 = __ballot_sync(0xFFFFFFFFu, a), n1 = __ballot_sync(0xFFFFFFFFu, b);
-		if (lane == 0) {
-			uint8_t st = 0;
-			uint32_t res = cur;
-			if (n0 != w0 || n1 != w1) { // changed
-				if ((n0 | n1) == 0u)
-					res = kNull;
-				else {
-					st = 1;
-					*reinterpret_cast<uint2 *>(lv.cand + size_t(item) * 2u) = make_uint2(n0, n1);
+		uint32_t o_res = m_cur, o_n0 = 0, o_n1 = 0;
+		uint8_t o_st = 0;
+		const uint32_t count = min(32u, n - base);
+		for (uint32_t k = 0; k < count; ++k) {
+			const uint32_t cur = __shfl_sync(full, m_cur, k), len = __shfl_sync(full, m_len, k);
+			const uint32_t *list = lv.lists + __shfl_sync(full, m_off, k);
+			const uint32_t w0 = __shfl_sync(full, m_w0, k), w1 = __shfl_sync(full, m_w1, k);
+			uint32_t x, y, z;
+			unpack_pos(__shfl_sync(full, m_pos, k), x, y, z);
+			const uint32_t vx = (x << 2) | ((lane >> 2) & 2u) | (lane & 1u);
+			const uint32_t vy = (y << 2) | ((lane >> 3) & 2u) | ((lane >> 1) & 1u);
+			const uint32_t vz = (z << 2) | ((lane >> 2) & 1u); // voxel l: z1 = 0; voxel l+32: z1 = 1 (adds 2)
+			bool a = w0 >> lane & 1u, b = w1 >> lane & 1u;
+			for (uint32_t j = 0; j < len; ++j) {
+				const hd_edit_desc &e = edits[list[j]];
+				bool ia, ib;
+				if (kTerrain && e.kind == HD_EDIT_TERRAIN_FILL && terrain_leaf_pair(e, x << 2, z << 2, vx, vy, vz, ia, ib)) { // warp-uniform
+					a = a || ia, b = b || ib;
+					continue;
 				}
+				edit_voxel_pair<kTerrain>(e, vx, vy, vz, a, b);
 			}
-			lv.state[item] = st;
-			lv.result[item] = res;
+			const uint32_t n0 = __ballot_sync(full, a), n1 = __ballot_sync(full, b);
+			if (lane == k && (n0 != w0 || n1 != w1)) { // changed
+				if ((n0 | n1) == 0u)
+					o_res = kNull;
+				else
+					o_st = 1, o_n0 = n0, o_n1 = n1;
+			}
+		}
+		if (mine < n) {
+			if (o_st)
+				*reinterpret_cast<uint2 *>(lv.cand + size_t(mine) * 2u) = make_uint2(o_n0, o_n1);
+			lv.state[mine] = o_st;
+			lv.result[mine] = o_res;
 		}
 	}
 }
@@ -1543,10 +1555,12 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 	if (deepest == L - 1) {
 		LevelAlloc &lv = levels[L - 1];
 		HD_CUDA_TRY(lv.init_up(true));
+		// one warp per 32 leaves; at least ~8 warps per SM-slot worth of grid so that small levels still spread out
+		const uint32_t leaf_grid = grid_for(uint64_t((lv.v.n + 31u) / 32u) * 32u);
 		if (terrain)
-			k_leaf<true><<<grid_for(uint64_t(lv.v.n) * 32), kBlock, 0, st>>>(g, p->words, edits_dev, lv.v, s->ctr);
+			k_leaf<true><<<leaf_grid, kBlock, 0, st>>>(g, p->words, edits_dev, lv.v, s->ctr);
 		else
-			k_leaf<false><<<grid_for(uint64_t(lv.v.n) * 32), kBlock, 0, st>>>(g, p->words, edits_dev, lv.v, s->ctr);
+			k_leaf<false><<<leaf_grid, kBlock, 0, st>>>(g, p->words, edits_dev, lv.v, s->ctr);
 		HD_LAUNCH_CHECK();
 		rs = run_upsert(p, L - 1, lv.v.n, 2, lv.v.cand, lv.v.state, lv.v.winner, lv.v.cur, lv.v.result);
 		if (rs != HD_OK)
