@@ -227,16 +227,18 @@ __device__ inline void write_list(const hd_edit_desc *__restrict__ edits, const 
 	}
 }
 
-// Allocate one slot in the next level (and `count` list entries) with warp-aggregated atomics.
-// Must be called by all 32 lanes of the warp (lanes without work pass want = false).
+// Allocate one slot in the next level (and `count` list entries): CTA-aggregated — ONE pair of atomics per CTA and trip.
+// (Per-warp aggregation put 2 x 7.5 M atomics on one cache line at the level above the leaves of the cfg3 batch:
+// ~8 of the kernel's 11.7 ms were the L2 atomic unit serialising them.)
+// Must be called by every thread of the CTA (threads without work pass want = false); `s_alloc` is 2 x 17 words of
+// shared memory.
+constexpr uint32_t kMaxWarps = 16;
 __device__ __forceinline__ bool alloc_item(DevCounters *ctr, uint32_t *items_ctr, uint32_t *entries_ctr, bool want,
                                            uint32_t count, uint32_t cap, uint32_t cap_entries, uint32_t &item,
-                                           uint32_t &entry_off) {
+                                           uint32_t &entry_off, uint32_t *s_alloc) {
 	const uint32_t full = 0xFFFFFFFFu;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31u) >> 5;
 	const uint32_t wants = __ballot_sync(full, want);
-	if (!wants)
-		return false;
-	const uint32_t lane = threadIdx.x & 31u;
 	uint32_t c = want ? count : 0u, scan = c; // inclusive warp scan of the list lengths
 #pragma unroll
 	for (int d = 1; d < 32; d <<= 1) {
@@ -244,16 +246,28 @@ __device__ __forceinline__ bool alloc_item(DevCounters *ctr, uint32_t *items_ctr
 		if (lane >= uint32_t(d))
 			scan += v;
 	}
-	const uint32_t total_entries = __shfl_sync(full, scan, 31);
-	uint32_t base_item = 0, base_entry = 0;
-	if (lane == 0) {
-		base_item = atomicAdd(items_ctr, __popc(wants));
-		base_entry = atomicAdd(entries_ctr, total_entries);
+	uint32_t *s_items = s_alloc, *s_entries = s_alloc + kMaxWarps + 1;
+	if (lane == 31u)
+		s_items[warp] = __popc(wants), s_entries[warp] = scan;
+	__syncthreads();
+	if (threadIdx.x == 0) { // exclusive scan over the warps' totals, one reservation for the whole CTA
+		uint32_t ti = 0, te = 0;
+		for (uint32_t w = 0; w < nwarps; ++w) {
+			const uint32_t a = s_items[w], b = s_entries[w];
+			s_items[w] = ti, s_entries[w] = te;
+			ti += a, te += b;
+		}
+		uint32_t bi = 0, be = 0;
+		if (ti) {
+			bi = atomicAdd(items_ctr, ti);
+			be = atomicAdd(entries_ctr, te);
+		}
+		s_items[kMaxWarps] = bi, s_entries[kMaxWarps] = be;
 	}
-	base_item = __shfl_sync(full, base_item, 0);
-	base_entry = __shfl_sync(full, base_entry, 0);
-	item = base_item + __popc(wants & ((1u << lane) - 1u));
-	entry_off = base_entry + scan - c;
+	__syncthreads();
+	item = s_items[kMaxWarps] + s_items[warp] + __popc(wants & ((1u << lane) - 1u));
+	entry_off = s_entries[kMaxWarps] + s_entries[warp] + scan - c;
+	__syncthreads(); // the next trip overwrites s_alloc
 	if (want && (item >= cap || entry_off + count > cap_entries)) {
 		ctr->error = 1;
 		return false;
@@ -414,10 +428,10 @@ __device__ __forceinline__ void phase_down(const Geometry &g, uint32_t level /* 
                                            const uint32_t *__restrict__ words, const hd_edit_desc *__restrict__ edits,
                                            const uint32_t *__restrict__ filled, const LevelView &in, const LevelView &out,
                                            DevCounters *ctr, uint32_t *items_ctr, uint32_t *entries_ctr, uint32_t tid0,
-                                           uint32_t nthreads) {
-	const uint32_t n8 = in.count() * 8u, lane = threadIdx.x & 31u;
+                                           uint32_t nthreads, uint32_t *s_alloc) {
+	const uint32_t n8 = in.count() * 8u;
 	const uint32_t bits = g.voxel_level() - (level + 1u);
-	for (uint32_t t = tid0; t - lane < n8; t += nthreads) {
+	for (uint32_t t = tid0; t - threadIdx.x < n8; t += nthreads) { // whole CTAs iterate together (alloc_item synchronises)
 		const uint32_t item = t >> 3, c = t & 7u;
 		const bool valid = t < n8;
 		Filtered f{kNull, 0u, 0u, 0u};
@@ -440,7 +454,7 @@ __device__ __forceinline__ void phase_down(const Geometry &g, uint32_t level /* 
 		}
 		uint32_t slot, entry_off;
 		const bool made = alloc_item(ctr, items_ctr, entries_ctr, valid && f.count != 0, f.count, out.cap, out.cap_entries,
-		                             slot, entry_off);
+		                             slot, entry_off, s_alloc);
 		if (!valid || len > 32u)
 			continue; // long lists: k_down_long
 		if (made) {
@@ -461,8 +475,9 @@ __global__ void __launch_bounds__(kBlock) k_down(Geometry g, uint32_t level, con
                                                  const hd_edit_desc *__restrict__ edits,
                                                  const uint32_t *__restrict__ filled, LevelView in, LevelView out,
                                                  DevCounters *ctr, uint32_t *items_ctr, uint32_t *entries_ctr) {
+	__shared__ uint32_t s_alloc[2 * (kMaxWarps + 1)];
 	phase_down<kTerrain>(g, level, words, edits, filled, in, out, ctr, items_ctr, entries_ctr, blockIdx.x * blockDim.x + threadIdx.x,
-	           gridDim.x * blockDim.x);
+	                     gridDim.x * blockDim.x, s_alloc);
 }
 
 // Leaf pass: one warp per 4x4x4 leaf (a persistent grid-stride variant measured 10-20 % slower: the per-leaf work is
@@ -1004,6 +1019,7 @@ struct FusedArgs {
 };
 __global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_constant__ FusedArgs a) {
 	__shared__ uint32_t s_cand[kFusedThreads / 32][12];
+	__shared__ uint32_t s_alloc[2 * (kMaxWarps + 1)];
 	__shared__ uint32_t s_first_big;
 	cg::grid_group grid = cg::this_grid();
 	const Geometry &g = a.g;
@@ -1026,7 +1042,7 @@ __global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_const
 		uint32_t l = 0;
 		for (; l + 1 < L && items[l] <= kSoloDown; ++l) {
 			phase_down<false>(g, l, a.words, edits, a.filled, a.lv[l], a.lv[l + 1], ctr, &ctr->lvl_items[l + 1],
-			                  &ctr->lvl_entries[l + 1], threadIdx.x, blockDim.x);
+			                  &ctr->lvl_entries[l + 1], threadIdx.x, blockDim.x, s_alloc);
 			__syncthreads();
 		}
 		if (threadIdx.x == 0)
@@ -1036,7 +1052,7 @@ __global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_const
 	// ---- stage B (grid): the remaining top-down levels ----
 	for (uint32_t l = *(volatile uint32_t *)&ctr->next_items; l + 1 < L; ++l) {
 		phase_down<false>(g, l, a.words, edits, a.filled, a.lv[l], a.lv[l + 1], ctr, &ctr->lvl_items[l + 1], &ctr->lvl_entries[l + 1],
-		                  gtid, gthreads);
+		                  gtid, gthreads, s_alloc);
 		grid.sync();
 	}
 	// ---- stage C (grid): bottom-up over the levels that are worth the grid; then CTA 0 finishes the small top ----
@@ -1209,6 +1225,25 @@ __global__ void __launch_bounds__(kBlock) k_bucket_scatter(uint32_t n, const uin
 	order[offset[b] + atomicAdd(&fill[b], 1u)] = item;
 }
 
+__device__ __forceinline__ uint32_t image_hash2(uint32_t w0, uint32_t w1) {
+	uint32_t h = (w0 * 0x9E3779B1u) ^ (w1 * 0x85EBCA77u);
+	return h ^ (h >> 15);
+}
+__device__ __forceinline__ uint32_t image_hashn(const uint32_t *w, uint32_t n) {
+	uint32_t h = n;
+	for (uint32_t i = 0; i < n; ++i)
+		h = (h ^ w[i]) * 0x9E3779B1u;
+	return h ^ (h >> 15);
+}
+__device__ __forceinline__ uint32_t image_hashn_reg(const uint32_t (&w)[9], uint32_t n) { // same value, registers only
+	uint32_t h = n;
+#pragma unroll
+	for (uint32_t i = 0; i < 9u; ++i)
+		if (i < n)
+			h = (h ^ w[i]) * 0x9E3779B1u;
+	return h ^ (h >> 15);
+}
+
 __global__ void __launch_bounds__(kGroupThreads) k_upsert_grouped(Geometry g, uint32_t level, bool fast_scan, uint32_t stride,
                                                                   const uint32_t *__restrict__ cand,
                                                                   const uint32_t *__restrict__ fallback, uint32_t *result,
@@ -1225,38 +1260,135 @@ __global__ void __launch_bounds__(kGroupThreads) k_upsert_grouped(Geometry g, ui
 	const uint32_t bucket = g.level_base[level] + b, base = bucket << g.bucket_shift();
 	const uint32_t bw = bucket_words[bucket], wpp = g.words_per_page(), wpb = g.words_per_bucket();
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	uint32_t *tab = img + wpb; // open-addressing index over the image: 0 = empty, else node position + 1 (wpb slots, <= 50 % full)
+	const uint32_t tmask = wpb - 1u;
+	const bool indexed = is_leaf || fast_scan;
 	for (uint32_t i = threadIdx.x; i < bw; i += kGroupThreads)
 		img[i] = words[base + i];
+	if (indexed)
+		for (uint32_t i = threadIdx.x; i < wpb; i += kGroupThreads)
+			tab[i] = 0u;
 	__syncthreads();
 
-	// phase A: every candidate of the bucket against the staged image (read-only)
-	for (uint32_t c = warp; c < cnt; c += kGroupThreads / 32) {
-		const uint32_t item = order[first + c];
-		const uint32_t *me = cand + size_t(item) * stride;
-		const uint32_t c0 = me[0], c1 = me[1];
-		const uint32_t nw = is_leaf ? 2u : 1u + __popc(c0 & 0xFFu);
-		uint32_t found = kMiss;
+	// phase A: every candidate of the bucket against the staged image (read-only).  A linear scan per candidate made
+	// this kernel shared-memory-bandwidth-bound (72 candidates x 8 KB per bucket at the 8^3-node level of the cfg3 batch),
+	// so the image is indexed once by content hash and every candidate costs one or two probes.
+	if (indexed) {
 		if (is_leaf) {
-			for (uint32_t off = 0; off < bw && found == kMiss; off += 64u) {
-				const uint32_t p = off + lane * 2u;
-				const bool hit = p + 2u <= bw && img[p] == c0 && img[p + 1] == c1;
-				const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
-				if (m)
-					found = base + off + (__ffs(m) - 1u) * 2u;
-			}
-		} else if (fast_scan) {
-			for (uint32_t off = 0; off < bw && found == kMiss; off += 32u) {
-				const uint32_t p = off + lane;
-				bool hit = p + nw <= bw && img[p] == c0;
-				if (hit)
-					for (uint32_t i = 1; i < nw && hit; ++i)
-						hit = img[p + i] == me[i];
-				const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
-				if (m)
-					found = base + off + __ffs(m) - 1u;
+			for (uint32_t q = threadIdx.x * 2u; q + 2u <= bw; q += kGroupThreads * 2u) {
+				const uint32_t w0 = img[q], w1 = img[q + 1u];
+				if ((w0 | w1) == 0u)
+					continue; // page-tail padding; an all-zero leaf is never stored (NodePool.hpp:337)
+				uint32_t slot = image_hash2(w0, w1) & tmask;
+				while (atomicCAS(&tab[slot], 0u, q + 1u) != 0u)
+					slot = (slot + 1u) & tmask;
 			}
 		} else {
-			if (lane == 0)
+			// a word <= 0xFF inside the used region is always a node header (child pointers are >= 256 here, padding is 0)
+			for (uint32_t q = threadIdx.x; q < bw; q += kGroupThreads) {
+				const uint32_t hw = img[q];
+				if (hw - 1u >= 0xFFu)
+					continue;
+				const uint32_t nw = 1u + __popc(hw);
+				if (q + nw > bw)
+					continue;
+				uint32_t slot = image_hashn(img + q, nw) & tmask;
+				while (atomicCAS(&tab[slot], 0u, q + 1u) != 0u)
+					slot = (slot + 1u) & tmask;
+			}
+		}
+		__syncthreads();
+		// Candidates in chunks of one per thread: (A) look up, (B1) thread 0 places the chunk's misses one after the other
+		// from their sizes in shared memory (the no-page-straddle rule makes placement sequential, but it never touches
+		// global memory), (B2) every thread writes its own node.  The former append loop — one warp, one miss at a time,
+		// each with its own global round trips — was what this kernel spent its time in.
+		__shared__ uint32_t s_nw[kGroupThreads], s_at[kGroupThreads], s_cur, s_app, s_ovf;
+		if (threadIdx.x == 0)
+			s_cur = bw, s_app = 0u, s_ovf = 0u;
+		for (uint32_t c0 = 0; c0 < cnt; c0 += kGroupThreads) {
+			const uint32_t c = c0 + threadIdx.x;
+			uint32_t item = 0, nw = 0, found = kMiss;
+			uint32_t w[9];
+			if (c < cnt) {
+				item = order[first + c];
+				const uint32_t *me = cand + size_t(item) * stride;
+				w[0] = me[0], w[1] = me[1];
+				nw = is_leaf ? 2u : 1u + __popc(w[0] & 0xFFu);
+#pragma unroll
+				for (uint32_t i = 2; i < 9u; ++i)
+					w[i] = i < nw ? me[i] : 0u;
+				uint32_t slot = (is_leaf ? image_hash2(w[0], w[1]) : image_hashn_reg(w, nw)) & tmask;
+				for (uint32_t v; (v = tab[slot]) != 0u; slot = (slot + 1u) & tmask) {
+					const uint32_t q = v - 1u;
+					bool same = img[q] == w[0] && img[q + 1u] == w[1];
+#pragma unroll
+					for (uint32_t i = 2; i < 9u; ++i)
+						same = same && (i >= nw || img[q + i] == w[i]);
+					if (same) {
+						found = base + q;
+						break;
+					}
+				}
+			}
+			s_nw[threadIdx.x] = (c < cnt && found == kMiss) ? nw : 0u;
+			__syncthreads();
+			if (threadIdx.x == 0) { // append_node placement, NodePool.hpp:134-157, in list order
+				uint32_t cur = s_cur, app = 0, ovf = 0;
+				const uint32_t m = min(uint32_t(kGroupThreads), cnt - c0);
+				for (uint32_t i = 0; i < m; ++i) {
+					const uint32_t k = s_nw[i];
+					if (k == 0u)
+						continue;
+					const uint32_t off = cur & (wpp - 1u);
+					const uint32_t at = off + k > wpp ? (cur | (wpp - 1u)) + 1u : cur; // never straddle a page; the tail stays zero
+					if (at + k > wpb) { // bucket full: keep the old node (NodePool.hpp:137-139,195)
+						s_at[i] = kMiss;
+						++ovf;
+						continue;
+					}
+					s_at[i] = at;
+					cur = at + k;
+					++app;
+				}
+				s_cur = cur, s_app += app, s_ovf += ovf;
+			}
+			__syncthreads();
+			if (c < cnt) {
+				if (found == kMiss) {
+					const uint32_t at = s_at[threadIdx.x];
+					if (at == kMiss)
+						found = fallback ? fallback[item] : kNull;
+					else {
+#pragma unroll
+						for (uint32_t i = 0; i < 9u; ++i)
+							if (i < nw)
+								words[base + at + i] = w[i];
+						found = base + at;
+					}
+				}
+				result[item] = found;
+			}
+			__syncthreads(); // s_nw / s_at are rewritten by the next chunk
+		}
+		if (threadIdx.x == 0) {
+			bucket_words[bucket] = s_cur;
+			atomicAdd(&ctr->stats[2], (unsigned long long)cnt);
+			atomicAdd(&ctr->stats[7], (unsigned long long)bw);
+			if (s_app) {
+				atomicAdd(&ctr->stats[3], (unsigned long long)s_app);
+				atomicAdd(&ctr->stats[4], (unsigned long long)(s_cur - bw));
+			}
+			if (s_ovf)
+				atomicAdd(&ctr->stats[5], (unsigned long long)s_ovf);
+		}
+		return;
+	} else {
+		for (uint32_t c = warp; c < cnt; c += kGroupThreads / 32) { // tiny configs: sequential walk by lane 0
+			const uint32_t item = order[first + c];
+			const uint32_t *me = cand + size_t(item) * stride;
+			const uint32_t nw = 1u + __popc(me[0] & 0xFFu);
+			uint32_t found = kMiss;
+			if (lane == 0) {
 				for (uint32_t page = 0; page < bw && found == kMiss; page += wpp) {
 					const uint32_t end = min(page + wpp, bw);
 					for (uint32_t it = page; nw <= end - it;) {
@@ -1274,10 +1406,9 @@ __global__ void __launch_bounds__(kGroupThreads) k_upsert_grouped(Geometry g, ui
 						it += sz;
 					}
 				}
-			found = __shfl_sync(0xFFFFFFFFu, found, 0);
+				result[item] = found;
+			}
 		}
-		if (lane == 0)
-			result[item] = found;
 	}
 	__syncthreads();
 
@@ -1374,7 +1505,14 @@ static hd_status run_upsert(hd_pool *p, uint32_t level, uint32_t n, uint32_t str
 		k_bucket_scatter<<<grid_for(n), kBlock, 0, p->stream>>>(n, state, bkt, offset, count, order);
 		HD_LAUNCH_CHECK();
 		// ...which ends up holding the per-bucket candidate count again
-		k_upsert_grouped<<<nb, kGroupThreads, size_t(p->geo.words_per_bucket()) * 4, p->stream>>>(
+		// dynamic shared memory: the bucket image + its content index (8 bytes per bucket word: 16 KB for 2 048-word buckets)
+		const size_t gsm = size_t(p->geo.words_per_bucket()) * 8;
+		static bool attr_set = false;
+		if (!attr_set && gsm > 48u * 1024u) {
+			HD_CUDA_TRY(cudaFuncSetAttribute(k_upsert_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGroupMaxWords) * 8));
+			attr_set = true;
+		}
+		k_upsert_grouped<<<nb, kGroupThreads, gsm, p->stream>>>(
 		    p->geo, level, s->fast_scan, stride, cand, fallback, result, p->words, p->bucket_words, offset, count, order, s->ctr);
 		HD_LAUNCH_CHECK();
 		cudaFreeAsync(bkt, p->stream), cudaFreeAsync(order, p->stream), cudaFreeAsync(count, p->stream), cudaFreeAsync(offset, p->stream);
