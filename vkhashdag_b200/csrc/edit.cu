@@ -544,6 +544,63 @@ __global__ void __launch_bounds__(kBlock, kTerrain ? 4 : 6) k_leaf(Geometry g, c
 	}
 }
 
+// Leaf pass for batches without a terrain edit: like k_leaf, but a HALF-warp works on a leaf (lane owns 4 voxels), so a
+// trip of the inner loop finishes two leaves and the per-leaf overhead (record shuffles, coordinate unpacking, loop
+// control, descriptor loads) is paid once per two.  Leaf bit i = [z1 y1 x1 z0 y0 x0] (NodeCoord.hpp:32-43): the lane's
+// low four bits are [x1 z0 y0 x0], its voxels are (y1, z1) in {0,1}^2.
+__global__ void __launch_bounds__(kBlock, 5) k_leaf_half(Geometry g, const uint32_t *__restrict__ words,
+                                                         const hd_edit_desc *__restrict__ edits, LevelView lv, DevCounters *ctr) {
+	const uint32_t lane = threadIdx.x & 31u, l16 = lane & 15u, half = lane >> 4, full = 0xFFFFFFFFu, n = lv.count();
+	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; base < n; base += warps * 32u) {
+		const uint32_t mine = base + lane;
+		uint32_t m_cur = kNull, m_off = 0, m_len = 0, m_w0 = 0, m_w1 = 0;
+		uint64_t m_pos = 0;
+		if (mine < n) {
+			m_cur = lv.cur[mine], m_off = lv.list_off[mine], m_len = lv.list_len[mine], m_pos = lv.pos[mine];
+			if (m_cur != kNull) {
+				const uint2 w = *reinterpret_cast<const uint2 *>(words + m_cur);
+				m_w0 = w.x, m_w1 = w.y;
+			}
+		}
+		uint32_t o_res = m_cur, o_n0 = 0, o_n1 = 0;
+		uint8_t o_st = 0;
+		const uint32_t count = min(32u, n - base);
+		for (uint32_t k = 0; k < count; k += 2u) {
+			const uint32_t src = k + half; // items beyond `count` have m_len == 0 and m_cur == kNull: nothing happens
+			const uint32_t len = __shfl_sync(full, m_len, src);
+			const uint32_t *list = lv.lists + __shfl_sync(full, m_off, src);
+			const uint32_t w0 = __shfl_sync(full, m_w0, src), w1 = __shfl_sync(full, m_w1, src);
+			uint32_t x, y, z;
+			unpack_pos(__shfl_sync(full, m_pos, src), x, y, z);
+			const uint32_t vx = (x << 2) | ((l16 >> 2) & 2u) | (l16 & 1u);
+			const uint32_t vy = (y << 2) | ((l16 >> 1) & 1u); // + 2 for y1
+			const uint32_t vz = (z << 2) | ((l16 >> 2) & 1u); // + 2 for z1
+			bool v[4] = {bool(w0 >> l16 & 1u), bool(w0 >> (l16 + 16u) & 1u), bool(w1 >> l16 & 1u), bool(w1 >> (l16 + 16u) & 1u)};
+			for (uint32_t j = 0; j < len; ++j)
+				edit_voxel_quad(edits[list[j]], vx, vy, vz, v);
+			const uint32_t b0 = __ballot_sync(full, v[0]), b1 = __ballot_sync(full, v[1]);
+			const uint32_t b2 = __ballot_sync(full, v[2]), b3 = __ballot_sync(full, v[3]);
+			if (lane == k || lane == k + 1u) { // the owner of the leaf half `lane - k` worked on
+				const uint32_t sh = (lane - k) << 4;
+				const uint32_t n0 = ((b0 >> sh) & 0xFFFFu) | ((b1 >> sh) << 16), n1 = ((b2 >> sh) & 0xFFFFu) | ((b3 >> sh) << 16);
+				if (n0 != m_w0 || n1 != m_w1) { // changed
+					if ((n0 | n1) == 0u)
+						o_res = kNull;
+					else
+						o_st = 1, o_n0 = n0, o_n1 = n1;
+				}
+			}
+		}
+		if (mine < n) {
+			if (o_st)
+				*reinterpret_cast<uint2 *>(lv.cand + size_t(mine) * 2u) = make_uint2(o_n0, o_n1);
+			lv.state[mine] = o_st;
+			lv.result[mine] = o_res;
+		}
+	}
+}
+
 // Bottom-up re-pack of inner items (edit_node tail, NodePool.hpp:384-395).  Thread per item.
 __device__ __forceinline__ void assemble_item(const uint32_t *__restrict__ words, const LevelView &lv, uint32_t item) {
 	const uint32_t cur = lv.cur[item];
@@ -1698,7 +1755,7 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 		if (terrain)
 			k_leaf<true><<<leaf_grid, kBlock, 0, st>>>(g, p->words, edits_dev, lv.v, s->ctr);
 		else
-			k_leaf<false><<<leaf_grid, kBlock, 0, st>>>(g, p->words, edits_dev, lv.v, s->ctr);
+			k_leaf_half<<<leaf_grid, kBlock, 0, st>>>(g, p->words, edits_dev, lv.v, s->ctr);
 		HD_LAUNCH_CHECK();
 		rs = run_upsert(p, L - 1, lv.v.n, 2, lv.v.cand, lv.v.state, lv.v.winner, lv.v.cur, lv.v.result);
 		if (rs != HD_OK)

@@ -247,6 +247,26 @@ __device__ __forceinline__ bool terrain_leaf_pair(const hd_edit_desc &d, uint32_
 	return true;
 }
 
+// The same for the four voxels a lane owns when a HALF-warp works on a leaf: (x, y + 2*j, z + 2*k), j, k in {0, 1};
+// in[j + 2*k].
+__device__ __forceinline__ void sphere_in_range_quad(const hd_edit_desc &d, uint32_t x, uint32_t y, uint32_t z, bool (&in)[4]) {
+	const int32_t dx = int32_t(x - d.p0[0]), dy = int32_t(y - d.p0[1]), dz = int32_t(z - d.p0[2]);
+	const uint32_t ax = uint32_t(dx < 0 ? -dx : dx), ay = uint32_t(dy < 0 ? -dy : dy) + 2u, az = uint32_t(dz < 0 ? -dz : dz) + 2u;
+	if (max(ax, max(ay, az)) < 37837u) {
+		const uint32_t sx = uint32_t(dx * dx);
+		const uint32_t sy0 = sx + uint32_t(dy * dy), sy1 = sx + uint32_t((dy + 2) * (dy + 2));
+		const uint32_t z0 = uint32_t(dz * dz), z1 = uint32_t((dz + 2) * (dz + 2));
+		in[0] = uint64_t(sy0 + z0) <= d.r2, in[1] = uint64_t(sy1 + z0) <= d.r2;
+		in[2] = uint64_t(sy0 + z1) <= d.r2, in[3] = uint64_t(sy1 + z1) <= d.r2;
+	} else {
+		const long long X = dx, Y = dy, Z = dz;
+		const uint64_t sx = uint64_t(X * X);
+		const uint64_t sy0 = sx + uint64_t(Y * Y), sy1 = sx + uint64_t((Y + 2) * (Y + 2));
+		const uint64_t z0 = uint64_t(Z * Z), z1 = uint64_t((Z + 2) * (Z + 2));
+		in[0] = sy0 + z0 <= d.r2, in[1] = sy1 + z0 <= d.r2, in[2] = sy0 + z1 <= d.r2, in[3] = sy1 + z1 <= d.r2;
+	}
+}
+
 // EditVoxel (main.cpp:60-63,133-142)
 template <bool kTerrain = true>
 __device__ __forceinline__ bool edit_voxel(const hd_edit_desc &d, uint32_t x, uint32_t y, uint32_t z, bool voxel) {
@@ -265,6 +285,22 @@ __device__ __forceinline__ void edit_voxel_pair(const hd_edit_desc &d, uint32_t 
 	} else {
 		a = edit_voxel<kTerrain>(d, x, y, z, a);
 		b = edit_voxel<kTerrain>(d, x, y, z + 2u, b);
+	}
+}
+
+// EditVoxel for a lane's four voxels of a leaf (half-warp per leaf, no terrain): v[j + 2*k] = voxel (x, y + 2j, z + 2k).
+__device__ __forceinline__ void edit_voxel_quad(const hd_edit_desc &d, uint32_t x, uint32_t y, uint32_t z, bool (&v)[4]) {
+	const uint32_t kind = d.kind;
+	if (kind == HD_EDIT_SPHERE_FILL || kind == HD_EDIT_SPHERE_DIG) {
+		bool in[4];
+		sphere_in_range_quad(d, x, y, z, in);
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			v[i] = kind == HD_EDIT_SPHERE_DIG ? (v[i] && !in[i]) : (v[i] || in[i]);
+	} else {
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			v[i] = edit_voxel<false>(d, x, y + 2u * (i & 1), z + (i & 2), v[i]);
 	}
 }
 
