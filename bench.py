@@ -288,7 +288,7 @@ def run_ours(args):
                 "note": "gather/latency-bound: dependent 4-byte loads; see profiles/ for L2 sectors and stall reasons"}
 
     # ---- edit throughput (secondary metric: edited voxels/s) measured on the scene build ----
-    edit = {"workload": f"terrain fill 2^{LEVEL_COUNT} in one batched pass", "seconds": round(build_s, 4),
+    edit = {"workload": f"terrain fill 2^{LEVEL_COUNT} in one batched pass (cold: the first GPU work of the process)", "seconds": round(build_s, 4),
             "visited_leaves": stats["visited_leaves"], "leaf_voxels_per_s": round(stats["visited_leaves"] * 64 / build_s),
             "appended_nodes": stats["appended_nodes"], "overflow_count": stats["overflow_count"]}
 
@@ -302,16 +302,21 @@ def run_ours(args):
         cfg3 = abi.custom_config(CFG3_BUCKET_BITS)
         vl3 = cfg3.voxel_level
         pool3 = v.DAGNodePool(cfg3, device=local)
-        root3 = pool3.Edit(abi.NULL, v.TerrainEditor(vl3, extent_bits=CFG3_PATCH_BITS))
-        assert pool3.last_stats["overflow_count"] == 0
         spheres = abi.random_spheres(EDIT_BATCH, vl3, seed=1234, rmin=16, rmax=256, extent_bits=CFG3_PATCH_BITS)
-        mirror = pool3.Download() if cpu_baseline is not None else None   # un-edited scene for the CPU editor (timed later)
         arr = abi.edit_array(spheres)
-        # the GPU idled while the host worked (CPU tracer leg, descriptor set-up): bring the clocks back up with a few
-        # untimed frames before the 0.1 s batch is timed
+        # One untimed rehearsal of the whole sequence first (the warm-up step of this one-shot workload): the GPU idled
+        # while the host ran the CPU tracer leg, and the first pass through the general edit path grows the stream-
+        # ordered allocator's pool by several GB.  Then the pool is cleared and the sequence is run again, timed.
+        pool3.EditBatch(pool3.Edit(abi.NULL, v.TerrainEditor(vl3, extent_bits=CFG3_PATCH_BITS)), arr)
+        pool3.Clear()
+        t0 = time.perf_counter()
+        root3 = pool3.Edit(abi.NULL, v.TerrainEditor(vl3, extent_bits=CFG3_PATCH_BITS))
+        edit["terrain_patch_warm_seconds"] = round(time.perf_counter() - t0, 4)
+        assert pool3.last_stats["overflow_count"] == 0
+        mirror = pool3.Download() if cpu_baseline is not None else None   # un-edited scene for the CPU editor (timed later)
         P3 = abi.camera_params(cfg3, root3, (0.06, 0.09, 0.06), 0.8, -0.5236, W4K, H4K, lod=False)
         with torch.cuda.stream(torch.cuda.ExternalStream(pool3.stream, device=local)):
-            for _ in range(40):
+            for _ in range(40):   # the download above let the clocks drop again
                 pool3.TraceDev(P3, rgba8=rgba.data_ptr())
             pool3.Sync()
         t0 = time.perf_counter()

@@ -110,6 +110,9 @@ struct hd_pool {
 
 	hd::EditScratch *edit = nullptr;
 
+	// pick ray (hd_traverse_ray): result block in mapped pinned host memory, written by the kernel itself
+	float *pick_host = nullptr, *pick_host_dev = nullptr;
+
 	// dirty-range scratch
 	uint32_t *dirty_scratch = nullptr; // [0]=n_ranges, [1]=payload words, then per-range data
 	uint64_t dirty_scratch_bytes = 0;

@@ -168,6 +168,7 @@ void hd_pool_destroy(hd_pool *p) {
 	cudaFree(p->stage_hits);
 	cudaFree(p->params_dev);
 	cudaFree(p->dirty_scratch);
+	cudaFreeHost(p->pick_host);
 	for (int i = 0; i < 2; ++i) {
 		cudaFree(p->pipe_rgba[i]);
 		if (p->pipe_traced[i])
