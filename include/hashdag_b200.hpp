@@ -211,6 +211,9 @@ public:
 		m_last_status = hd_edit_batch(m_pool, *root, edits, n, &out, &m_last_stats);
 		return m_last_status == HD_OK ? NodePointer<uint32_t>{out} : root;
 	}
+	// Which implementation served the last Edit / EditBatch: 0 = general level-synchronous pass, 1 = the one-launch
+	// low-latency path batches of <= 32 sphere/AABB editors take (the interactive brush), 2 = the same as a CUDA graph.
+	uint32_t GetLastEditPath() const { return hd_edit_last_path(m_pool); }
 
 	// NodePoolTraversal::Traversal<float> (NodePoolTraversal.hpp:93-256), the pick ray of main.cpp:320-321
 	template <typename F = float> std::optional<Vec3> Traversal(NodePointer<uint32_t> root, Vec3 o, Vec3 d) const {

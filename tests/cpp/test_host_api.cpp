@@ -102,6 +102,7 @@ int main() {
 		CHECK(!pool->Traversal<float>(root, {0.5f, 0.5f, 1.5f}, {0.5145f, 0.f, -0.8575f}));
 		CHECK(!pool->Traversal<float>({}, {0.5f, 0.5f, 1.5f}, {0.f, 0.f, -1.f}));
 		auto dug = pool->Edit(root, SphereEditor<EditMode::kDig>{{512, 512, 853}, 40ull * 40ull});
+		CHECK(pool->GetLastEditPath() == 1); // a single brush editor takes the one-launch low-latency path
 		CHECK(dug && dug != root);
 		auto hit2 = pool->Traversal<float>(dug, {0.5f, 0.5f, 1.5f}, {0.f, 0.f, -1.f});
 		CHECK(hit2 && hit2->z < hit->z);
