@@ -186,8 +186,8 @@ def test_bucket_full_and_no_page_straddle(oracle, hd, top_bits):
 
 def test_brush_sequence_low_latency_path(oracle, hd):
     """The interactive loop (src/main.cpp:214-238): one brush editor per call, fill/dig alternating, on a terrain.
-    Every call is served by the low-latency path (one CUDA graph, device-resident queue counts) and the DAG after the
-    whole sequence is canonically equal to sequential CPU edits."""
+    Every call is served by the low-latency path (one cooperative kernel — or, with HD_EDIT_FAST=2, one CUDA graph — and
+    device-resident queue counts) and the DAG after the whole sequence is canonically equal to sequential CPU edits."""
     cfg = abi.default_config(level_count=9, top_level_count=9)
     vl = cfg.voxel_level
     res = 1 << vl
@@ -204,14 +204,14 @@ def test_brush_sequence_low_latency_path(oracle, hd):
     assert dev.last_stats["path"] == "general"          # terrain fills always take the general path
     for e in edits[1:]:
         groot = dev.EditBatch(groot, [e])
-        assert dev.last_stats["path"] == "fused" and dev.last_stats["overflow_count"] == 0
+        assert dev.last_stats["path"] in ("fused", "graph") and dev.last_stats["overflow_count"] == 0
     exp = opool.canonical(oroot)
     got, _ = device_canonical(oracle, dev, cfg, groot)
     assert got["hash"] == exp["hash"] and got["by_ptr"] == got["by_content"] == exp["by_ptr"]
     assert got["voxels"] == exp["voxels"] and got["per_level"] == exp["per_level"]
     # a small multi-editor batch (<= 32) is one graph launch too, and order inside it is honoured
     g2 = dev.EditBatch(groot, edits[1:9])
-    assert dev.last_stats["path"] == "fused"
+    assert dev.last_stats["path"] in ("fused", "graph")
     o2 = opool.edit_batch(oroot, edits[1:9])
     assert device_canonical(oracle, dev, cfg, g2)[0]["hash"] == opool.canonical(o2)["hash"]
     dev.close()
@@ -233,7 +233,7 @@ r = dev.EditBatch(abi.NULL, edits[:1])
 assert dev.last_stats["path"] == "general", dev.last_stats     # work queues of 64 items cannot hold this sphere
 used = dev.UsedWords()
 r = dev.EditBatch(r, edits[1:])
-assert dev.last_stats["path"] == "fused", dev.last_stats       # the small brush fits
+assert dev.last_stats["path"] in ("fused", "graph"), dev.last_stats       # the small brush fits
 mirror = O.pool(cfg)
 ranges, bw = dev.Download()
 for off, words in ranges.items():
