@@ -257,3 +257,31 @@ def test_low_latency_queue_overflow_falls_back(oracle, hd):
     out = subprocess.run([sys.executable, "-c", _OVERFLOW_SCRIPT.format(root=root)], env=env, capture_output=True,
                          text=True, timeout=300)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_degenerate_edits(oracle, hd):
+    """Edge cases of the editor contract on the GPU paths (one call per edit -> low-latency path; one batch; and a batch
+    padded past 32 editors -> general path): single-voxel and zero-volume edits, edits clipped by or outside the world,
+    whole-world fill and clear, digging in empty space, repeated edits."""
+    cfg = abi.default_config(level_count=6, top_level_count=9)
+    res = 1 << cfg.voxel_level
+    edits = [
+        abi.sphere((5, 5, 5), 9, dig=True), abi.sphere((10, 11, 12), 0), abi.aabb((3, 3, 3), (3, 9, 9)),
+        abi.aabb((res - 1, res - 1, res - 1), (res, res, res)), abi.sphere((res - 1, res - 1, res - 1), 50),
+        abi.sphere((10, 11, 12), 0), abi.aabb((1, 2, 3), (40, 50, 60)),
+        abi.sphere((res // 2, res // 2, res // 2), 7 ** 2, dig=True), abi.aabb((1, 2, 3), (4, 5, 6)),
+    ]
+    check_equal(oracle, hd, cfg, edits, batches=[1] * len(edits))[0].close()
+    check_equal(oracle, hd, cfg, edits)[0].close()
+    padded = edits + [abi.sphere((20, 20, 20), 4, dig=True)] * 30      # 39 editors: the general path
+    dev = check_equal(oracle, hd, cfg, padded)[0]
+    assert dev.last_stats["path"] == "general"
+    dev.close()
+    # whole world, then everything away again: filled root, then Null, on the low-latency path
+    dev = hd.DAGNodePool(cfg)
+    r = dev.EditBatch(NULL, [abi.aabb((0, 0, 0), (res, res, res))])
+    assert r == dev.FilledNodes()[0]
+    r = dev.EditBatch(r, [abi.sphere((res // 2,) * 3, (3 * res) ** 2, dig=True)])
+    assert r == NULL
+    assert dev.EditBatch(NULL, []) == NULL                                # empty batch: root unchanged
+    dev.close()

@@ -110,3 +110,60 @@ def test_colour_pool_decode(oracle, ref):
         assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (x, y, z)
         checked += 1
     assert checked > 300
+
+
+def test_degenerate_edits_pointer_exact(oracle, ref):
+    """Edge cases of the editor contract, restatement vs the reference's headers, pointer for pointer: single-voxel and
+    zero-volume edits, edits entirely outside the world, whole-world fill and clear, digging in empty space, the same
+    edit twice (idempotence), and a centre on the world's far corner."""
+    cfg = B.default_config(level_count=6, top_level_count=9)
+    res = 1 << cfg.voxel_level
+    edits = [
+        B.sphere((5, 5, 5), 9, dig=True),                       # dig in an empty world -> Null stays Null
+        B.sphere((10, 11, 12), 0),                              # r2 = 0: exactly one voxel
+        B.aabb((3, 3, 3), (3, 9, 9)),                           # empty box (lo == hi on one axis)
+        B.aabb((res - 1, res - 1, res - 1), (res, res, res)),   # the last voxel of the world
+        B.sphere((res - 1, res - 1, res - 1), 50),              # ball clipped by three faces
+        B.sphere((10, 11, 12), 0),                              # again: nothing changes
+        B.aabb((0, 0, 0), (res, res, res)),                     # whole world -> the filled root
+        B.sphere((res // 2, res // 2, res // 2), 7 ** 2, dig=True),
+        B.sphere((res // 2, res // 2, res // 2), (3 * res) ** 2, dig=True),  # everything away again -> Null
+        B.aabb((1, 2, 3), (4, 5, 6)),
+    ]
+    op, rp = oracle.pool(cfg), ref.pool(cfg)
+    ro = rr = B.NULL
+    seen = []
+    for e in edits:
+        ro, rr = op.edit(ro, e), rp.edit(rr, e)
+        assert ro == rr
+        seen.append(ro)
+    assert seen[0] == B.NULL and seen[2] == seen[1] and seen[5] == seen[4]
+    assert seen[6] == op.filled_nodes()[0] == rp.filled_nodes()[0] and seen[8] == B.NULL
+    assert np.array_equal(op.bucket_words_np(), rp.bucket_words_np())
+    for off, cnt in op.used_ranges():
+        assert np.array_equal(op.words_np(off, cnt), rp.words_np(off, cnt))
+
+
+def test_bucket_overflow_fallback_pointer_exact(oracle, ref):
+    """Collisions: with one 32-word bucket per level the pool overflows almost at once; a full bucket keeps the OLD
+    node (NodePool.hpp:137-139,195) and both sides must agree on every pointer, every bucket cursor and every word —
+    including the zeroed page tails a node would have straddled."""
+    cfg = B.HdConfig()
+    cfg.word_bits_per_page, cfg.page_bits_per_bucket, cfg.node_levels = 4, 1, 4
+    for l in range(4):
+        cfg.bucket_bits_each_level[l] = 1 if l < 3 else 2
+    res = 1 << (cfg.node_levels + 1)
+    rng = np.random.default_rng(23)
+    op, rp = oracle.pool(cfg), ref.pool(cfg)
+    ro = rr = B.NULL
+    for _ in range(40):
+        c = [int(v) for v in rng.integers(0, res, 3)]
+        r = int(rng.integers(1, res // 2))
+        e = B.sphere(c, r * r, dig=bool(rng.random() < 0.3)) if rng.random() < 0.7 else \
+            B.aabb(c, [min(res, v + int(rng.integers(1, res // 2))) for v in c])
+        ro, rr = op.edit(ro, e), rp.edit(rr, e)
+        assert ro == rr
+    assert op.stats()["overflow"] > 0                        # the case was actually exercised
+    assert np.array_equal(op.bucket_words_np(), rp.bucket_words_np())
+    for off, cnt in op.used_ranges():
+        assert np.array_equal(op.words_np(off, cnt), rp.words_np(off, cnt))
