@@ -77,6 +77,7 @@ class Oracle(_Lib):
         L.orc_terrain_height.restype = u32
         L.orc_terrain_height.argtypes = [C.POINTER(HdEditDesc), u32, u32]
         L.orc_canonical.argtypes = [pu32, u32, u32, C.POINTER(u64)]
+        L.orc_canonical_fast.argtypes = [pu32, C.POINTER(HdConfig), u32, u32, C.POINTER(u64)]
         L.orc_count_stored_nodes.argtypes = [pu32, pu32, C.POINTER(HdConfig), C.POINTER(u64)]
         L.orc_voxel_get.restype = C.c_int
         L.orc_voxel_get.argtypes = [pu32, u32, u32, u32, u32, u32]
@@ -110,6 +111,13 @@ class Oracle(_Lib):
         self.lib.orc_canonical(words_ptr, node_levels, root, out)
         return {"hash": out[0], "by_ptr": out[1], "by_content": out[2], "voxels": out[3],
                 "per_level": [out[4 + i] for i in range(node_levels)]}
+
+    def canonical_fast(self, words_ptr, cfg, root, threads=0):
+        """Same dict as canonical(), computed level by level on `threads` host threads (bench-scale pools)."""
+        out = (C.c_uint64 * (4 + cfg.node_levels))()
+        self.lib.orc_canonical_fast(words_ptr, C.byref(cfg), root, threads, out)
+        return {"hash": out[0], "by_ptr": out[1], "by_content": out[2], "voxels": out[3],
+                "per_level": [out[4 + i] for i in range(cfg.node_levels)]}
 
     def count_stored_nodes(self, pool):
         """[stored node count per level] by walking every bucket of a host pool/mirror."""

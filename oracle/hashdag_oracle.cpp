@@ -962,6 +962,154 @@ void orc_canonical(const uint32_t *words, uint32_t node_levels, uint32_t root, u
 	out[3] = c.count(root, 0);
 }
 
+// The same canonical description, level-synchronous and multi-threaded, for bench-scale pools (10^7..10^8 reachable
+// nodes, where the memoised recursion above needs minutes and several GB of hash maps).  Reachable pointers are marked
+// in one bitmap per level (top-down), ranked by prefix popcounts, and content hashes / voxel counts are computed
+// bottom-up into dense arrays indexed by rank.  Values are identical to orc_canonical's (tests/test_oracle_golden.py).
+extern "C++" {
+namespace {
+template <class F> void parallel_for(uint64_t n, uint32_t threads, uint64_t grain, F f) {
+	if (n == 0)
+		return;
+	threads = std::max(1u, std::min<uint32_t>(threads, uint32_t((n + grain - 1) / grain)));
+	std::atomic<uint64_t> next{0};
+	auto work = [&]() {
+		for (;;) {
+			uint64_t b = next.fetch_add(grain);
+			if (b >= n)
+				return;
+			f(b, std::min(n, b + grain));
+		}
+	};
+	std::vector<std::thread> ts;
+	for (uint32_t t = 1; t < threads; ++t)
+		ts.emplace_back(work);
+	work();
+	for (auto &t : ts)
+		t.join();
+}
+
+struct LevelSet {
+	uint64_t base = 0, n_words = 0; // word range of the level in the pool
+	uint64_t *bits = nullptr;       // one bit per pool word of the level
+	std::vector<uint32_t> prefix;   // set bits before each 64-bit bitmap word
+	uint64_t count = 0;
+	uint64_t rank(uint32_t ptr) const {
+		const uint64_t i = ptr - base;
+		return prefix[i >> 6] + uint64_t(__builtin_popcountll(bits[i >> 6] & ((1ull << (i & 63)) - 1ull)));
+	}
+	template <class F> void for_each(uint32_t threads, F f) const { // f(ptr, rank)
+		parallel_for((n_words + 63) / 64, threads, 1u << 14, [&](uint64_t b, uint64_t e) {
+			for (uint64_t w = b; w < e; ++w) {
+				uint64_t m = bits[w], r = prefix[w];
+				while (m) {
+					const uint32_t k = uint32_t(__builtin_ctzll(m));
+					m &= m - 1;
+					f(uint32_t(base + (w << 6) + k), r++);
+				}
+			}
+		});
+	}
+};
+
+uint64_t count_distinct(std::vector<uint64_t> &v, uint32_t threads) {
+	if (v.size() < (1u << 16)) {
+		std::sort(v.begin(), v.end());
+		return uint64_t(std::unique(v.begin(), v.end()) - v.begin());
+	}
+	// partition by the top 8 bits, sort the partitions in parallel
+	std::vector<uint64_t> cnt(257, 0), out(v.size());
+	for (uint64_t x : v)
+		++cnt[(x >> 56) + 1];
+	for (int i = 0; i < 256; ++i)
+		cnt[i + 1] += cnt[i];
+	std::vector<uint64_t> pos(cnt.begin(), cnt.end() - 1);
+	for (uint64_t x : v)
+		out[pos[x >> 56]++] = x;
+	std::atomic<uint64_t> distinct{0};
+	parallel_for(256, threads, 1, [&](uint64_t b, uint64_t e) {
+		for (uint64_t i = b; i < e; ++i) {
+			std::sort(out.begin() + cnt[i], out.begin() + cnt[i + 1]);
+			distinct += uint64_t(std::unique(out.begin() + cnt[i], out.begin() + cnt[i + 1]) - (out.begin() + cnt[i]));
+		}
+	});
+	return distinct;
+}
+} // namespace
+} // extern "C++"
+
+void orc_canonical_fast(const uint32_t *words, const hd_config *cfg, uint32_t root, uint32_t threads, uint64_t *out) {
+	Geometry g;
+	const uint32_t L = cfg->node_levels;
+	for (uint32_t i = 0; i < 4 + L; ++i)
+		out[i] = 0;
+	if (!make_geometry(*cfg, g) || root == kNull)
+		return;
+	threads = threads ? threads : std::max(1u, std::thread::hardware_concurrency());
+	std::vector<LevelSet> S(L);
+	for (uint32_t l = 0; l < L; ++l) {
+		S[l].base = uint64_t(g.level_base[l]) << g.bucket_shift();
+		S[l].n_words = (1ull << cfg->bucket_bits_each_level[l]) << g.bucket_shift();
+		S[l].bits = static_cast<uint64_t *>(std::calloc((S[l].n_words + 63) / 64, 8));
+	}
+	auto finish_level = [&](LevelSet &s) {
+		const uint64_t nw = (s.n_words + 63) / 64;
+		s.prefix.resize(nw);
+		uint64_t acc = 0;
+		for (uint64_t w = 0; w < nw; ++w)
+			s.prefix[w] = uint32_t(acc), acc += uint64_t(__builtin_popcountll(s.bits[w]));
+		s.count = acc;
+	};
+	// top-down marking
+	S[0].bits[(root - S[0].base) >> 6] |= 1ull << ((root - S[0].base) & 63);
+	for (uint32_t l = 0; l < L; ++l) {
+		finish_level(S[l]);
+		if (l + 1 == L)
+			break;
+		LevelSet &c = S[l + 1];
+		S[l].for_each(threads, [&](uint32_t ptr, uint64_t) {
+			const uint32_t mask = words[ptr] & 0xFFu;
+			for (uint32_t k = 1, n = 1 + uint32_t(__builtin_popcount(mask)); k < n; ++k) {
+				const uint64_t i = words[ptr + k] - c.base;
+				__atomic_fetch_or(&c.bits[i >> 6], 1ull << (i & 63), __ATOMIC_RELAXED);
+			}
+		});
+	}
+	// bottom-up hashes and voxel counts (Canon::hash / Canon::count above, value for value)
+	std::vector<uint64_t> H_child, V_child, H, V;
+	for (uint32_t l = L; l-- > 0;) {
+		const LevelSet &s = S[l];
+		H.assign(s.count, 0), V.assign(s.count, 0);
+		if (l == L - 1) {
+			s.for_each(threads, [&](uint32_t ptr, uint64_t r) {
+				H[r] = mix64(0x1eafull ^ (uint64_t(words[ptr]) | uint64_t(words[ptr + 1]) << 32));
+				V[r] = uint64_t(__builtin_popcount(words[ptr]) + __builtin_popcount(words[ptr + 1]));
+			});
+		} else {
+			const LevelSet &c = S[l + 1];
+			s.for_each(threads, [&](uint32_t ptr, uint64_t r) {
+				const uint32_t mask = words[ptr] & 0xFFu;
+				uint64_t h = mix64(0x1234567ull + mask + (uint64_t(l) << 32)), v = 0;
+				uint32_t k = 1;
+				for (uint32_t i = 0; i < 8; ++i)
+					if (mask >> i & 1u) {
+						const uint64_t cr = c.rank(words[ptr + k++]);
+						h = mix64(h ^ (H_child[cr] + 0x9e3779b97f4a7c15ull * (i + 1)));
+						v += V_child[cr];
+					}
+				H[r] = h, V[r] = v;
+			});
+		}
+		out[1] += s.count, out[4 + l] = s.count;
+		if (l == 0)
+			out[0] = H[0], out[3] = V[0];
+		H_child = H, V_child.swap(V);
+		out[2] += count_distinct(H, threads);
+	}
+	for (auto &s : S)
+		std::free(s.bits);
+}
+
 // Nodes physically stored in a pool (walk of every bucket, node sizes as find_node_in_span steps them,
 // NodePool.hpp:79-91): out[level] = stored node count.  Used to prove a GC left no unreachable node behind.
 void orc_count_stored_nodes(const uint32_t *words, const uint32_t *bucket_words, const hd_config *cfg, uint64_t *out) {

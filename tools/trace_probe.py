@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""tools/trace_probe.py — quick A/B of trace-kernel variants on the cfg2 scene (GPU box; also the ncu target).
+
+  HD_TRACE_VARIANT=1 python tools/trace_probe.py --frames 20          device-timed Mrays/s, full detail and LOD
+  ncu --set full --import-source on -k regex:trace_kernel -s 4 -c 1 -o gpurun_out/x python tools/trace_probe.py --frames 2
+
+Checks every variant's frames against variant-independent checksums printed with the numbers (same scene, same cameras),
+so two runs can be compared by eye: equal checksums = identical pixels.
+"""
+import argparse
+import json
+import os
+import sys
+import zlib
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import vkhashdag_b200 as v  # noqa: E402
+from vkhashdag_b200 import abi  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=20)
+    ap.add_argument("--level", type=int, default=15)
+    ap.add_argument("--lod", action="store_true")
+    a = ap.parse_args()
+    bench.LEVEL_COUNT = a.level
+    cfg = bench.scene_config()
+    pool = v.DAGNodePool(cfg, device=0)
+    root = pool.Edit(abi.NULL, v.TerrainEditor(cfg.voxel_level))
+    assert pool.last_stats["overflow_count"] == 0
+    W, H = bench.W4K, bench.H4K
+    stream = torch.cuda.ExternalStream(pool.stream, device=0)
+    rgba = torch.zeros(W * H, dtype=torch.int32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    out = {}
+    for lod in ((False, True) if a.lod else (False,)):
+        ev, crc = [], 0
+        with torch.cuda.stream(stream):
+            for s in range(-3, a.frames):
+                P = bench.camera(cfg, root, s + 1000 * lod, W, H, lod)
+                flush.fill_(s & 0xFF)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                pool.TraceDev(P, rgba8=rgba.data_ptr())
+                e1.record()
+                if s >= 0:
+                    ev.append((e0, e1))
+                if s in (0, a.frames - 1):
+                    pool.Sync()
+                    crc = zlib.crc32(rgba.cpu().numpy().tobytes(), crc)
+            torch.cuda.synchronize()
+        ms = [x.elapsed_time(y) for x, y in ev]
+        out["lod" if lod else "full"] = {"Mrays_s": round(W * H * len(ms) / sum(ms) / 1e3, 1), "ms_min": round(min(ms), 4),
+                                         "ms_max": round(max(ms), 4), "crc": crc}
+    print(json.dumps({"variant": os.environ.get("HD_TRACE_VARIANT", "0"), "level": a.level, **out}))
+    pool.close()
+
+
+if __name__ == "__main__":
+    main()

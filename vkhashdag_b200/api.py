@@ -317,6 +317,27 @@ class DAGNodePool:
         shift = self.config.word_bits_per_page + self.config.page_bits_per_bucket
         return {int(b) << shift: self.ReadWords(int(b) << shift, int(bw[b])) for b in np.nonzero(bw)[0]}, bw
 
+    def DownloadInto(self, host_pool, chunk_words=1 << 26):
+        """Mirror the device pool into a host pool object (words_np(offset, count) / bucket_words_np() views, e.g. a
+        ReadPage/WritePage-style mirror): runs of consecutive non-empty buckets are read as whole buckets straight into
+        the mirror's memory (a bucket's unused tail is zero on the device).  Returns the words read."""
+        bw = self.ReadBucketWords()
+        host_pool.bucket_words_np()[:] = bw
+        shift = self.config.word_bits_per_page + self.config.page_bits_per_bucket
+        nz = np.flatnonzero(bw)
+        if nz.size == 0:
+            return 0
+        cuts = np.flatnonzero(np.diff(nz) > 1) + 1
+        total = 0
+        for run in np.split(nz, cuts):
+            off, cnt = int(run[0]) << shift, (int(run[-1]) - int(run[0]) + 1) << shift
+            for o in range(off, off + cnt, chunk_words):
+                c = min(chunk_words, off + cnt - o)
+                dst = host_pool.words_np(o, c)
+                _check(self._L.hd_pool_read_words(self._h, o, dst.ctypes.data, c))
+                total += c
+        return total
+
     def UsedWords(self):
         out = C.c_uint64()
         _check(self._L.hd_pool_used_words(self._h, C.byref(out)))
