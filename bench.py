@@ -43,7 +43,8 @@ BOTTOM_BUCKET_BITS = 17   # DefaultConfig with 2^17 buckets per bottom level: th
 TILE = 64
 ROW_STEP = 24             # CPU legs trace every 24th row of a 4K frame (90 rows = 345 600 rays per frame)
 COLOR_LEAF_LEVEL = 10     # DAGColorPool::Config::leaf_level of src/main.cpp:206
-COLOR_SPHERES = 1200      # paint spheres of the headline scene's colour pool
+COLOR_SPHERES = 300       # paint spheres of the headline scene's colour pool (each re-encodes up to ~2 500 colour leaves: ~1.3 M
+                          # chunk words per sphere, and the 30-bit leaf index of DAGColorPool.hpp:23-34 caps the pool at 2^30 words)
 EDIT_BATCH = 10000        # sphere edits of BASELINE.json config 3
 # cfg3 = "2^17 terrain with 10k edits".  A FULL 2^17 x 2^17 terrain of this noise function does not fit the reference's
 # address space: the 2^16 x 2^16 patch below stores 528.6 M words of 8^3-voxel nodes (level 14, measured with the
