@@ -248,10 +248,16 @@ hd_status hd_traverse_ray(hd_pool *pool, uint32_t root, const float o[3], const 
 
 /* ---- replica sync: replaces DAGNodePool::Flush for the multi-GPU case ----
  * Buckets are append-only, so the dirty set is [words at last sync, bucket_words) of every bucket.  The editing
- * rank packs it into one staging buffer (u32 words)
- *   [n_ranges][payload_words][root][clear_first]  n_ranges x {word_offset, word_count, payload_offset}  payload...
+ * rank packs it into one staging buffer (u32 words, 8-word header)
+ *   [n_ranges][payload_words][root][flags][n_color_ranges][color_payload_words][color_root][color_leaf_level]
+ *   n_ranges x {word_offset, word_count, payload_offset}  payload...  [colour section]
  * which the caller broadcasts (one NCCL broadcast over NVLink); replicas apply it with a scatter kernel that also
- * advances their bucket_words, and publish the root last. */
+ * advances their bucket_words, and publish the root last.  flags: bit 0 = clear the replica first (after hd_gc), bit 1 =
+ * a colour section follows the node payload (the DAGColorPool delta since the last hd_dirty_reset: appended nodes,
+ * appended leaf chunks, chunks rewritten in place — replaces DAGColorPool::Flush, src/main.cpp:245-251), bit 2 = that
+ * section is the whole colour pool.  The total size is a function of the header alone (replica.packed_bytes).
+ * hd_dirty_apply_dev bounds-checks every range against the pool, its bucket and the payload before writing and returns
+ * HD_ERR_INVALID (root not published) for a malformed blob. */
 hd_status hd_dirty_count(hd_pool *pool, uint32_t *n_ranges, uint64_t *packed_bytes);
 hd_status hd_dirty_ranges(hd_pool *pool, hd_dirty_range *out, uint32_t capacity, uint32_t *n_out);
 hd_status hd_dirty_pack_dev(hd_pool *pool, void *staging_dev, uint64_t capacity_bytes, uint64_t *packed_bytes);

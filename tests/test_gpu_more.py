@@ -68,7 +68,7 @@ def test_replica_sync_pack_apply_same_device(oracle, hd):
         root = a.EditBatch(root, edits)
         a.SetRoot(root)
         n_ranges, need = a.DirtyCount()
-        assert n_ranges > 0 and sum(c for _, c in a.DirtyRanges()) * 4 + 16 + 12 * n_ranges == need
+        assert n_ranges > 0 and sum(c for _, c in a.DirtyRanges()) * 4 + 32 + 12 * n_ranges == need
         n = a.DirtyPack(stage.data_ptr(), stage.numel())
         assert n == need
         a.DirtyReset()
@@ -158,3 +158,21 @@ def test_two_gpu_replica_if_available(oracle, hd):
     P = abi.camera_params(cfg, root, (0.5, 0.8, 0.5), 0.6, -0.6, 256, 144)
     assert np.array_equal(a.Trace(P)["hits"], b.Trace(P)["hits"])
     a.close(), b.close()
+
+
+def test_torchrun_two_gpu_nccl_replica_sync():
+    """One process per GPU under torchrun (2 ranks): scene built on rank 0 and published with the NCCL dirty-range
+    broadcast (replaces DAGNodePool::Flush, src/DAGNodePool.cpp:56-85, for the replicated pool), then per frame a brush
+    edit on rank 0 -> ONE broadcast -> tile-sharded trace; the stitched frame must equal rank 0's full-frame trace and
+    every replica must hold the same bucket cursors and root (ordering contract of src/main.cpp:281-296)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29547", os.path.join(root, "tools", "multi_gpu_check.py"), "--level", "11", "--frames", "4",
+           "--width", "1280", "--height", "720"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MULTI-GPU CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

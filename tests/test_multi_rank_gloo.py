@@ -1,7 +1,7 @@
 """N > 1 host logic on CPU (gloo, world_size 2): the tile partition and the replica-sync protocol.
 
 The pool here is a host-memory stand-in that speaks the same staging format as sync.cu
-([n_ranges][payload_words][root][0] | {offset,count,payload_offset} x n | payload): the test checks that
+(8-word header [n_ranges][payload_words][root][flags][colour x 4] | {offset,count,payload_offset} x n | payload): the test checks that
 ReplicaSync drives it correctly under a real process group (ONE eager broadcast when the payload fits the eager
 chunk, one more for the remainder when it does not, staging growth on both sides, root last)."""
 import os
@@ -42,19 +42,19 @@ class HostPool:
 
     def DirtyCount(self):
         r = self._ranges()
-        return len(r), 4 * (4 + 3 * len(r) + sum(c for _, c in r))
+        return len(r), 4 * (8 + 3 * len(r) + sum(c for _, c in r))
 
     def DirtyPack(self, ptr, capacity):
         r = self._ranges()
-        n_words = 4 + 3 * len(r) + sum(c for _, c in r)
+        n_words = 8 + 3 * len(r) + sum(c for _, c in r)
         if 4 * n_words > capacity:   # same contract as hd_dirty_pack_dev: report the size, change nothing
             raise replica.StagingTooSmall(4 * n_words)
         buf = np.ctypeslib.as_array((np.ctypeslib.ctypes.c_uint32 * n_words).from_address(ptr))
-        buf[:4] = [len(r), sum(c for _, c in r), self.root, 0]
+        buf[:8] = [len(r), sum(c for _, c in r), self.root, 0, 0, 0, 0xC0000000, 0]
         poff = 0
-        payload0 = 4 + 3 * len(r)
+        payload0 = 8 + 3 * len(r)
         for i, (off, cnt) in enumerate(r):
-            buf[4 + 3 * i:7 + 3 * i] = [off, cnt, poff]
+            buf[8 + 3 * i:11 + 3 * i] = [off, cnt, poff]
             buf[payload0 + poff:payload0 + poff + cnt] = self.words[off:off + cnt]
             poff += cnt
         return 4 * n_words
@@ -62,9 +62,10 @@ class HostPool:
     def DirtyApply(self, ptr, nbytes):
         buf = np.ctypeslib.as_array((np.ctypeslib.ctypes.c_uint32 * (nbytes // 4)).from_address(ptr))
         n = int(buf[0])
-        payload0 = 4 + 3 * n
+        assert nbytes == replica.packed_bytes(buf)
+        payload0 = 8 + 3 * n
         for i in range(n):
-            off, cnt, poff = (int(v) for v in buf[4 + 3 * i:7 + 3 * i])
+            off, cnt, poff = (int(v) for v in buf[8 + 3 * i:11 + 3 * i])
             self.words[off:off + cnt] = buf[payload0 + poff:payload0 + poff + cnt]
             b = off >> self.shift
             self.bw[b] = self.synced[b] = (off & ((1 << self.shift) - 1)) + cnt
@@ -81,7 +82,7 @@ def _worker(rank, world, port, q):
     pool = HostPool()
     # rounds 0-2: tiny staging + tiny eager chunk -> grow path and the two-collective path;
     # rounds 3-5: roomy eager chunk -> exactly one collective per publish
-    sync = replica.ReplicaSync(pool, dist, device="cpu", capacity_bytes=64)
+    sync = replica.ReplicaSync(pool, dist, device="cpu", capacity_bytes=64, eager_bytes=32)
     rng = np.random.default_rng(42)
     for round_ in range(6):
         if round_ == 3:
@@ -94,7 +95,7 @@ def _worker(rank, world, port, q):
                 if pool.bw[b] + n <= 64:
                     pool.root = pool.append(b, rng.integers(1, 2 ** 32, n, dtype=np.uint64).astype(np.uint32))
         nbytes = sync.publish(src=0)
-        assert nbytes >= 16
+        assert nbytes >= 32
     assert sync.collectives == 3
     # tile partition: each rank owns t % world == rank; together they cover the frame exactly once
     W, H, T = 200, 130, 64

@@ -425,6 +425,23 @@ __global__ void k_leaf_alloc(CItems leaf, uint32_t first_leaf, uint32_t n_leaves
 	leaf.result[item] = res;
 }
 
+// replica sync: chunks that were rewritten IN PLACE below the already-synchronised part of the leaf array are not covered
+// by the append range, so their word indices go on the pool's dirty list (sync.cu packs them)
+__global__ void __launch_bounds__(kCB) k_color_mark_dirty(const uint32_t *__restrict__ chunk_idx, uint32_t n_leaves, uint32_t synced_words,
+                                                          uint32_t *list, uint32_t *ctr, uint32_t cap) {
+	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+	if (li >= n_leaves)
+		return;
+	const uint32_t idx = chunk_idx[li];
+	if (idx == 0xFFFFFFFFu || idx >= synced_words)
+		return;
+	const uint32_t slot = atomicAdd(&ctr[0], 1u);
+	if (slot < cap)
+		list[slot] = idx;
+	else
+		ctr[1] = 1u;
+}
+
 __global__ void __launch_bounds__(kCB) k_zero_weights(uint32_t n_leaves, const uint32_t *__restrict__ chunk_idx, uint32_t *cleaves) {
 	for (uint32_t li = blockIdx.x; li < n_leaves; li += gridDim.x) {
 		const uint32_t idx = chunk_idx[li];
@@ -509,11 +526,16 @@ struct CLevel {
 	}
 };
 
-static hd_status ensure_color_storage(hd_pool *p, uint64_t node_words, uint64_t leaf_words) {
+hd_status ensure_color_storage(hd_pool *p, uint64_t node_words, uint64_t leaf_words) {
 	cudaStream_t s = p->stream;
 	if (!p->color_ctr) {
 		HD_CUDA_TRY(cudaMalloc(&p->color_ctr, 4 * sizeof(uint32_t)));
 		HD_CUDA_TRY(cudaMemset(p->color_ctr, 0, 4 * sizeof(uint32_t)));
+	}
+	if (!p->color_dirty_list) {
+		HD_CUDA_TRY(cudaMalloc(&p->color_dirty_list, size_t(kColorDirtyCap) * sizeof(uint32_t)));
+		HD_CUDA_TRY(cudaMalloc(&p->color_dirty_ctr, 2 * sizeof(uint32_t)));
+		HD_CUDA_TRY(cudaMemset(p->color_dirty_ctr, 0, 2 * sizeof(uint32_t)));
 	}
 	auto grow = [&](uint32_t *&buf, uint64_t &cap, uint64_t used, uint64_t need) -> hd_status {
 		if (need + 8 <= cap)
@@ -564,6 +586,7 @@ hd_status hd_color_config(hd_pool *p, uint32_t leaf_level, uint32_t color_root) 
 	if (!p || leaf_level + 2 > p->geo.node_levels)
 		return HD_ERR_INVALID; // the colour leaf level must lie above the geometry leaf nodes
 	p->color_leaf_level = leaf_level, p->color_root = color_root;
+	p->color_dirty = true;
 	return HD_OK;
 }
 uint32_t hd_color_root(const hd_pool *p) { return p ? p->color_root : HD_COLOR_NULL; }
@@ -713,6 +736,9 @@ hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, 
 				k_leaf_alloc<<<cblocks(nl), kCB, 0, s>>>(leaf.v, first, nl, sbits, flag, fscan, bits, bscan, p->color_leaves, p->color_ctr,
 				                                        p->color_leaf_cap, chunk_idx);
 				HD_LAUNCH_CHECK();
+				k_color_mark_dirty<<<cblocks(nl), kCB, 0, s>>>(chunk_idx, nl, uint32_t(std::min<uint64_t>(p->color_synced_leaf_words, 0xFFFFFFFFull)),
+				                                              p->color_dirty_list, p->color_dirty_ctr, kColorDirtyCap);
+				HD_LAUNCH_CHECK();
 				k_zero_weights<<<std::min<uint32_t>(nl, 1184u), kCB, 0, s>>>(nl, chunk_idx, p->color_leaves);
 				HD_LAUNCH_CHECK();
 				k_emit<<<cblocks(n), kCB, 0, s>>>(n, sbits, colors, bw, flag, fscan, bscan, chunk_idx, p->color_leaves);
@@ -762,6 +788,7 @@ hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, 
 		return HD_ERR_OOM;
 	}
 	p->color_root = new_color_root;
+	p->color_dirty = true;
 	*color_root_out = new_color_root;
 
 	// ---- geometry (SphereEditor<kPaint> leaves the voxels alone, main.cpp:133-136) ----

@@ -79,6 +79,8 @@ struct hd_pool {
 	hd_config cfg{};
 	hd::Geometry geo{};
 	int device = 0;
+	int sm_count = 0;               // SMs of `device` (grids are sized per device, not per process)
+	bool grouped_smem_attr = false; // cudaFuncSetAttribute(k_upsert_grouped, MaxDynamicSharedMemorySize) done on `device`
 	cudaStream_t stream = nullptr;
 
 	uint32_t *words = nullptr;        // flat word space, SURVEY App. A.1 (device)
@@ -90,6 +92,12 @@ struct hd_pool {
 	uint64_t color_node_cap = 0, color_leaf_cap = 0;     // allocated words
 	uint32_t color_root = HD_COLOR_NULL, color_leaf_level = 0;
 	uint32_t *color_ctr = nullptr; // device: [0] = nodes used, [1] = leaf words used, [2] = out-of-space flag
+	// colour replica sync (sync.cu): nodes and appended leaf chunks are append-only, chunks rewritten in place since the
+	// last sync are listed on the device (color.cu appends to the list)
+	uint64_t color_synced_node_words = 0, color_synced_leaf_words = 0;
+	bool color_dirty = false;       // colour root / buffers changed since the last hd_dirty_reset
+	bool color_full_resync = false; // replicas must take the whole colour pool (hd_color_upload, dirty list overflow)
+	uint32_t *color_dirty_list = nullptr, *color_dirty_ctr = nullptr; // device: chunk word indices; [0] = count, [1] = overflow
 
 	uint32_t root = HD_NULL_NODE;
 	bool needs_full_resync = false; // set by hd_gc: replicas must clear before applying the next sync
@@ -126,4 +134,6 @@ hd_status upsert_batch_dev(hd_pool *pool, uint32_t level, uint32_t n, uint32_t s
 hd_status set_filled(hd_pool *pool, const std::vector<uint32_t> &filled);
 // device-wide exclusive prefix sum over u32 (color.cu); in == out is allowed
 hd_status exclusive_scan(hd_pool *pool, const uint32_t *in, uint32_t *out, uint64_t n);
+constexpr uint32_t kColorDirtyCap = 1u << 20; // entries of hd_pool::color_dirty_list
+hd_status ensure_color_storage(hd_pool *p, uint64_t node_words, uint64_t leaf_words); // color.cu
 } // namespace hd

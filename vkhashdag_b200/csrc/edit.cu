@@ -1176,9 +1176,7 @@ __global__ void k_fill_u8(uint8_t *out, uint32_t n, uint8_t v) {
 static inline uint32_t grid_for(uint64_t threads) { return uint32_t((threads + kBlock - 1) / kBlock); }
 // persistent grid for warp-per-item kernels: a multiple of the SM count, capped by the work
 static inline uint32_t upsert_grid(hd_pool *p, uint32_t n) {
-	static int sms = 0;
-	if (!sms)
-		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+	const int sms = std::max(p->sm_count, 1);
 	const uint64_t need = (uint64_t(n) * 32 + kBlock - 1) / kBlock;
 	return uint32_t(std::min<uint64_t>(need, uint64_t(sms) * 8));
 }
@@ -1223,12 +1221,21 @@ static hd_status scratch_init(hd_pool *p) {
 	if (p->edit)
 		return HD_OK;
 	auto *s = new EditScratch();
-	p->edit = s;
-	HD_CUDA_TRY(cudaMalloc(&s->ctr, sizeof(DevCounters)));
-	HD_CUDA_TRY(cudaMemset(s->ctr, 0, sizeof(DevCounters)));
-	HD_CUDA_TRY(cudaMalloc(&s->filled_dev, sizeof(uint32_t) * HD_MAX_NODE_LEVELS));
+	// p->edit is published only when every allocation succeeded: a half-initialised scratch would make the next call skip
+	// this function and dereference null device pointers
+	cudaError_t e = cudaMalloc(&s->ctr, sizeof(DevCounters));
+	if (e == cudaSuccess)
+		e = cudaMemset(s->ctr, 0, sizeof(DevCounters));
+	if (e == cudaSuccess)
+		e = cudaMalloc(&s->filled_dev, sizeof(uint32_t) * HD_MAX_NODE_LEVELS);
+	if (e != cudaSuccess) {
+		cudaFree(s->ctr), cudaFree(s->filled_dev);
+		delete s;
+		HD_CUDA_TRY(e);
+	}
 	// child pointers of any level >= 1 are >= (buckets at level 0) << bucket_shift
 	s->fast_scan = (uint64_t(1) << (p->geo.bucket_bits[0] + p->geo.bucket_shift())) >= 256ull;
+	p->edit = s;
 	return HD_OK;
 }
 
@@ -1564,10 +1571,9 @@ static hd_status run_upsert(hd_pool *p, uint32_t level, uint32_t n, uint32_t str
 		// ...which ends up holding the per-bucket candidate count again
 		// dynamic shared memory: the bucket image + its content index (8 bytes per bucket word: 16 KB for 2 048-word buckets)
 		const size_t gsm = size_t(p->geo.words_per_bucket()) * 8;
-		static bool attr_set = false;
-		if (!attr_set && gsm > 48u * 1024u) {
+		if (!p->grouped_smem_attr && gsm > 48u * 1024u) { // a per-device attribute: kept in the pool, not in a process static
 			HD_CUDA_TRY(cudaFuncSetAttribute(k_upsert_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGroupMaxWords) * 8));
-			attr_set = true;
+			p->grouped_smem_attr = true;
 		}
 		k_upsert_grouped<<<nb, kGroupThreads, gsm, p->stream>>>(
 		    p->geo, level, s->fast_scan, stride, cand, fallback, result, p->words, p->bucket_words, offset, count, order, s->ctr);
@@ -1799,9 +1805,7 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 
 // ---- low-latency path ------------------------------------------------------------------------------------------
 static uint32_t fast_grid(hd_pool *p, uint64_t threads) {
-	static int sms = 0;
-	if (!sms)
-		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+	const int sms = std::max(p->sm_count, 1);
 	return uint32_t(std::max<uint64_t>(1, std::min<uint64_t>((threads + kBlock - 1) / kBlock, uint64_t(sms) * 8)));
 }
 

@@ -8,12 +8,15 @@
 //
 //   mark (top-down)     level lists of unique reachable pointers; children are deduplicated through a scratch
 //                       open-addressing set (atomicCAS on the pointer value).
-//   rebuild (bottom-up) per level: gather the marked nodes with their children remapped through the level-below map,
-//                       zero the used part of the level's buckets, find-or-insert everything again with the edit
-//                       path's batched upsert (hash -> bucket -> lock-free append), record old -> new in a hash map.
+//   rebuild (bottom-up) into a FRESH word space allocated beside the old one: per level gather the marked nodes with their
+//                       children remapped through the level-below map, find-or-insert them with the edit path's batched
+//                       upsert (hash -> bucket -> lock-free append), record old -> new in a hash map.  The new arrays
+//                       replace the old ones only when every node found a place (a full bucket -> HD_ERR_OVERFLOW with
+//                       the pool untouched); hd_pool_words_dev / hd_pool_bucket_words_dev change across a successful GC.
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace hd {
 
@@ -125,20 +128,6 @@ __global__ void k_gc_lookup(const uint32_t *__restrict__ keys, const uint32_t *_
 		io[i] = vals[map_find_slot(keys, mask, io[i])];
 }
 
-// zero the used prefix of every bucket of one level and reset its cursor (one CTA per bucket, grid-stride)
-__global__ void __launch_bounds__(kGcBlock) k_gc_clear_level(uint32_t *words, uint32_t *bucket_words, uint32_t first_bucket,
-                                                             uint32_t n_buckets, uint32_t bucket_shift) {
-	for (uint32_t b = blockIdx.x; b < n_buckets; b += gridDim.x) {
-		const uint32_t bucket = first_bucket + b, used = bucket_words[bucket];
-		uint32_t *base = words + (size_t(bucket) << bucket_shift);
-		for (uint32_t i = threadIdx.x; i < used; i += blockDim.x)
-			base[i] = 0u;
-		__syncthreads();
-		if (threadIdx.x == 0)
-			bucket_words[bucket] = 0u;
-	}
-}
-
 template <typename T> static cudaError_t gmalloc(T **p, uint64_t count, cudaStream_t s) {
 	return cudaMallocAsync(reinterpret_cast<void **>(p), std::max<uint64_t>(count, 1) * sizeof(T), s);
 }
@@ -157,6 +146,49 @@ struct GcLevel {
 	uint32_t mask = 0;
 };
 
+// number of kNull results of a batched upsert (a full bucket: the rebuilt node could not be stored)
+__global__ void __launch_bounds__(kGcBlock) k_gc_count_null(const uint32_t *__restrict__ result, uint32_t n, uint32_t *count) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool bad = i < n && result[i] == kNull;
+	const uint32_t vote = __ballot_sync(0xFFFFFFFFu, bad);
+	if (vote && (threadIdx.x & 31u) == 0)
+		atomicAdd(count, __popc(vote));
+}
+
+namespace {
+// Everything hd_gc allocates; released on every exit path (the early returns of HD_CUDA_TRY included).
+struct GcState {
+	hd_pool *p;
+	cudaStream_t s;
+	std::vector<GcLevel> lv;
+	uint32_t *count_dev = nullptr, *seeds_dev = nullptr, *cand = nullptr, *result = nullptr, *io = nullptr;
+	uint32_t *new_words = nullptr, *new_bw = nullptr; // the compacted pool is built here; swapped in only on success
+	uint32_t *old_words = nullptr, *old_bw = nullptr;
+	bool swapped_in = false, committed = false;
+	~GcState() {
+		for (auto &l : lv) {
+			if (l.list)
+				cudaFreeAsync(l.list, s);
+			if (l.keys)
+				cudaFreeAsync(l.keys, s);
+			if (l.vals)
+				cudaFreeAsync(l.vals, s);
+		}
+		uint32_t *tmp[] = {count_dev, seeds_dev, cand, result, io};
+		for (uint32_t *q : tmp)
+			if (q)
+				cudaFreeAsync(q, s);
+		cudaStreamSynchronize(s);
+		if (swapped_in && !committed) // failure after the swap: the old pool is untouched, put it back
+			p->words = old_words, p->bucket_words = old_bw;
+		if (committed)
+			cudaFree(old_words), cudaFree(old_bw);
+		else
+			cudaFree(new_words), cudaFree(new_bw);
+	}
+};
+} // namespace
+
 } // namespace hd
 
 using namespace hd;
@@ -172,23 +204,12 @@ extern "C" hd_status hd_gc(hd_pool *p, const uint32_t *roots, uint32_t n_roots, 
 	const Geometry &g = p->geo;
 	const uint32_t L = g.node_levels;
 	cudaStream_t s = p->stream;
-	std::vector<GcLevel> lv(L);
-	uint32_t *count_dev = nullptr, *seeds_dev = nullptr;
-	HD_CUDA_TRY(gmalloc(&count_dev, 1, s));
-	HD_CUDA_TRY(gmalloc(&seeds_dev, n_roots + 1, s));
+	GcState G{p, s};
+	std::vector<GcLevel> &lv = G.lv;
+	lv.resize(L);
+	HD_CUDA_TRY(gmalloc(&G.count_dev, 1, s));
+	HD_CUDA_TRY(gmalloc(&G.seeds_dev, n_roots + 1, s));
 	uint64_t total = 0;
-	auto cleanup = [&]() {
-		for (auto &l : lv) {
-			if (l.list)
-				cudaFreeAsync(l.list, s);
-			if (l.keys)
-				cudaFreeAsync(l.keys, s);
-			if (l.vals)
-				cudaFreeAsync(l.vals, s);
-		}
-		cudaFreeAsync(count_dev, s), cudaFreeAsync(seeds_dev, s);
-		cudaStreamSynchronize(s);
-	};
 
 	// ---- mark (forward pass, NodePoolThreadedGC.hpp:72-103) ----
 	for (uint32_t l = 0; l < L; ++l) {
@@ -196,7 +217,6 @@ extern "C" hd_status hd_gc(hd_pool *p, const uint32_t *roots, uint32_t n_roots, 
 		const uint64_t cap = l == 0 ? uint64_t(n_roots) + 1 : uint64_t(lv[l - 1].n) * 8 + 1;
 		if (cap > 0xFFFFFFF0ull) {
 			set_error("gc: level %u too large", l);
-			cleanup();
 			return HD_ERR_OVERFLOW;
 		}
 		const uint64_t ts = table_size(cap);
@@ -204,77 +224,96 @@ extern "C" hd_status hd_gc(hd_pool *p, const uint32_t *roots, uint32_t n_roots, 
 		HD_CUDA_TRY(gmalloc(&lv[l].list, cap, s));
 		HD_CUDA_TRY(gmalloc(&lv[l].keys, ts, s));
 		HD_CUDA_TRY(cudaMemsetAsync(lv[l].keys, 0xFF, ts * 4, s));
-		HD_CUDA_TRY(cudaMemsetAsync(count_dev, 0, 4, s));
+		HD_CUDA_TRY(cudaMemsetAsync(G.count_dev, 0, 4, s));
 		std::vector<uint32_t> seeds;
 		if (l == 0)
 			seeds.assign(roots, roots + n_roots);
 		seeds.push_back(p->filled[l]);
-		HD_CUDA_TRY(cudaMemcpyAsync(seeds_dev, seeds.data(), seeds.size() * 4, cudaMemcpyHostToDevice, s));
+		HD_CUDA_TRY(cudaMemcpyAsync(G.seeds_dev, seeds.data(), seeds.size() * 4, cudaMemcpyHostToDevice, s));
 		HD_CUDA_TRY(cudaStreamSynchronize(s)); // seeds is a stack vector
-		k_gc_seed<<<1, 32, 0, s>>>(lv[l].keys, lv[l].mask, seeds_dev, uint32_t(seeds.size()), lv[l].list, count_dev);
+		k_gc_seed<<<1, 32, 0, s>>>(lv[l].keys, lv[l].mask, G.seeds_dev, uint32_t(seeds.size()), lv[l].list, G.count_dev);
 		HD_LAUNCH_CHECK();
 		if (l > 0 && lv[l - 1].n) {
 			k_gc_expand<<<gblocks(uint64_t(lv[l - 1].n) * 8), kGcBlock, 0, s>>>(p->words, lv[l - 1].list, lv[l - 1].n, lv[l].keys,
-			                                                                 lv[l].mask, lv[l].list, count_dev);
+			                                                                 lv[l].mask, lv[l].list, G.count_dev);
 			HD_LAUNCH_CHECK();
 		}
-		HD_CUDA_TRY(cudaMemcpyAsync(&lv[l].n, count_dev, 4, cudaMemcpyDeviceToHost, s));
+		HD_CUDA_TRY(cudaMemcpyAsync(&lv[l].n, G.count_dev, 4, cudaMemcpyDeviceToHost, s));
 		HD_CUDA_TRY(cudaStreamSynchronize(s));
 		total += lv[l].n;
 	}
 
-	// ---- rebuild (backward pass, NodePoolThreadedGC.hpp:276-348) ----
+	// ---- rebuild (backward pass, NodePoolThreadedGC.hpp:276-348) into a FRESH word space ----
+	// Remapped child pointers change every inner node's hash, so bucket loads are re-randomised and a bucket of a nearly
+	// full pool can overflow during the rebuild.  The compacted pool is therefore built beside the old one and swapped
+	// in only when every node found a place; on overflow the call returns HD_ERR_OVERFLOW and the pool is unchanged.
+	HD_CUDA_TRY(cudaMalloc(&G.new_words, g.total_words * sizeof(uint32_t)));
+	HD_CUDA_TRY(cudaMalloc(&G.new_bw, size_t(g.total_buckets) * sizeof(uint32_t)));
+	HD_CUDA_TRY(cudaMemsetAsync(G.new_words, 0, g.total_words * sizeof(uint32_t), s));
+	HD_CUDA_TRY(cudaMemsetAsync(G.new_bw, 0, size_t(g.total_buckets) * sizeof(uint32_t), s));
+	G.old_words = p->words, G.old_bw = p->bucket_words;
+	p->words = G.new_words, p->bucket_words = G.new_bw; // upsert_batch_dev appends into the pool's current arrays
+	G.swapped_in = true;
 	for (uint32_t l = L; l-- > 0;) {
 		const bool is_leaf = l == L - 1;
 		const uint32_t n = lv[l].n, stride = is_leaf ? 2u : 9u;
-		uint32_t *cand = nullptr, *result = nullptr;
-		HD_CUDA_TRY(gmalloc(&cand, uint64_t(n) * stride, s));
-		HD_CUDA_TRY(gmalloc(&result, n, s));
+		HD_CUDA_TRY(gmalloc(&G.cand, uint64_t(n) * stride, s));
+		HD_CUDA_TRY(gmalloc(&G.result, n, s));
 		if (n) {
-			k_gc_gather<<<gblocks(n), kGcBlock, 0, s>>>(p->words, lv[l].list, n, is_leaf, is_leaf ? nullptr : lv[l + 1].keys,
-			                                          is_leaf ? nullptr : lv[l + 1].vals, is_leaf ? 0u : lv[l + 1].mask, cand);
+			k_gc_gather<<<gblocks(n), kGcBlock, 0, s>>>(G.old_words, lv[l].list, n, is_leaf, is_leaf ? nullptr : lv[l + 1].keys,
+			                                          is_leaf ? nullptr : lv[l + 1].vals, is_leaf ? 0u : lv[l + 1].mask, G.cand);
 			HD_LAUNCH_CHECK();
 		}
-		const uint32_t nb = 1u << g.bucket_bits[l];
-		k_gc_clear_level<<<std::min<uint32_t>(nb, 148u * 16u), kGcBlock, 0, s>>>(p->words, p->bucket_words, g.level_base[l], nb,
-		                                                                      g.bucket_shift());
-		HD_LAUNCH_CHECK();
-		st = upsert_batch_dev(p, l, n, stride, cand, result);
-		if (st != HD_OK) {
-			cudaFreeAsync(cand, s), cudaFreeAsync(result, s);
-			cleanup();
+		st = upsert_batch_dev(p, l, n, stride, G.cand, G.result);
+		if (st != HD_OK)
 			return st;
+		if (n) { // a full bucket leaves kNull in result[]: publishing it would put Null children under set mask bits
+			uint32_t lost = 0;
+			HD_CUDA_TRY(cudaMemsetAsync(G.count_dev, 0, 4, s));
+			k_gc_count_null<<<gblocks(n), kGcBlock, 0, s>>>(G.result, n, G.count_dev);
+			HD_LAUNCH_CHECK();
+			HD_CUDA_TRY(cudaMemcpyAsync(&lost, G.count_dev, 4, cudaMemcpyDeviceToHost, s));
+			HD_CUDA_TRY(cudaStreamSynchronize(s));
+			// test hook: HD_GC_INJECT_OVERFLOW_LEVEL=l pretends level l lost a node (tests/test_gpu_gc_io.py checks that the
+			// pool survives a failed compaction untouched)
+			if (const char *inj = getenv("HD_GC_INJECT_OVERFLOW_LEVEL"))
+				if (uint32_t(atoi(inj)) == l)
+					lost = std::max(lost, 1u);
+			if (lost) {
+				set_error("gc: %u node(s) of level %u found their bucket full during the rebuild; the pool is unchanged", lost, l);
+				return HD_ERR_OVERFLOW;
+			}
 		}
 		// the mark set of this level becomes its old -> new map
 		HD_CUDA_TRY(gmalloc(&lv[l].vals, uint64_t(lv[l].mask) + 1, s));
 		if (n) {
-			k_gc_map_fill<<<gblocks(n), kGcBlock, 0, s>>>(lv[l].list, result, n, lv[l].keys, lv[l].vals, lv[l].mask);
+			k_gc_map_fill<<<gblocks(n), kGcBlock, 0, s>>>(lv[l].list, G.result, n, lv[l].keys, lv[l].vals, lv[l].mask);
 			HD_LAUNCH_CHECK();
 		}
-		cudaFreeAsync(cand, s), cudaFreeAsync(result, s);
+		cudaFreeAsync(G.cand, s), cudaFreeAsync(G.result, s);
+		G.cand = G.result = nullptr;
 	}
 
 	// ---- remap roots and filled nodes (tiny lookup kernels) ----
 	std::vector<uint32_t> filled(L);
+	std::vector<uint32_t> mapped(std::max(n_roots, 1u), kNull);
 	{
-		uint32_t *io = nullptr;
 		const uint32_t n_io = std::max(n_roots, 1u);
-		HD_CUDA_TRY(gmalloc(&io, n_io, s));
+		HD_CUDA_TRY(gmalloc(&G.io, n_io, s));
 		for (uint32_t l = 0; l < L; ++l) {
-			HD_CUDA_TRY(cudaMemcpyAsync(io, &p->filled[l], 4, cudaMemcpyHostToDevice, s));
-			k_gc_lookup<<<1, 32, 0, s>>>(lv[l].keys, lv[l].vals, lv[l].mask, io, 1);
+			HD_CUDA_TRY(cudaMemcpyAsync(G.io, &p->filled[l], 4, cudaMemcpyHostToDevice, s));
+			k_gc_lookup<<<1, 32, 0, s>>>(lv[l].keys, lv[l].vals, lv[l].mask, G.io, 1);
 			HD_LAUNCH_CHECK();
-			HD_CUDA_TRY(cudaMemcpyAsync(&filled[l], io, 4, cudaMemcpyDeviceToHost, s));
+			HD_CUDA_TRY(cudaMemcpyAsync(&filled[l], G.io, 4, cudaMemcpyDeviceToHost, s));
 			HD_CUDA_TRY(cudaStreamSynchronize(s));
 		}
 		if (n_roots) {
-			HD_CUDA_TRY(cudaMemcpyAsync(io, roots, size_t(n_roots) * 4, cudaMemcpyHostToDevice, s));
-			k_gc_lookup<<<gblocks(n_roots), kGcBlock, 0, s>>>(lv[0].keys, lv[0].vals, lv[0].mask, io, n_roots);
+			HD_CUDA_TRY(cudaMemcpyAsync(G.io, roots, size_t(n_roots) * 4, cudaMemcpyHostToDevice, s));
+			k_gc_lookup<<<gblocks(n_roots), kGcBlock, 0, s>>>(lv[0].keys, lv[0].vals, lv[0].mask, G.io, n_roots);
 			HD_LAUNCH_CHECK();
-			HD_CUDA_TRY(cudaMemcpyAsync(new_roots, io, size_t(n_roots) * 4, cudaMemcpyDeviceToHost, s));
+			HD_CUDA_TRY(cudaMemcpyAsync(mapped.data(), G.io, size_t(n_roots) * 4, cudaMemcpyDeviceToHost, s));
 			HD_CUDA_TRY(cudaStreamSynchronize(s));
 		}
-		cudaFreeAsync(io, s);
 	}
 	uint32_t root_new = p->root;
 	if (p->root != kNull) {
@@ -282,19 +321,21 @@ extern "C" hd_status hd_gc(hd_pool *p, const uint32_t *roots, uint32_t n_roots, 
 		root_new = kNull;
 		for (uint32_t i = 0; i < n_roots; ++i)
 			if (roots[i] == p->root)
-				root_new = new_roots[i];
+				root_new = mapped[i];
 	}
-	cleanup();
-	if (st != HD_OK)
-		return st;
-	st = set_filled(p, filled);
-	if (st != HD_OK)
-		return st;
-	p->root = root_new;
 	// every pointer changed: replicas need the whole pool again, after clearing theirs
 	HD_CUDA_TRY(cudaMemsetAsync(p->bucket_synced, 0, size_t(g.total_buckets) * 4, s));
 	HD_CUDA_TRY(cudaStreamSynchronize(s));
+	// ---- commit: nothing below can fail with the new pool half-published ----
+	G.committed = true;
+	for (uint32_t i = 0; i < n_roots; ++i)
+		new_roots[i] = mapped[i];
+	p->root = root_new;
 	p->needs_full_resync = true;
+	edit_scratch_free(p); // the low-latency edit path caches the pool's array addresses (arena locks, captured graph)
+	st = set_filled(p, filled);
+	if (st != HD_OK)
+		return st;
 	if (reachable_nodes)
 		*reachable_nodes = total;
 	return HD_OK;

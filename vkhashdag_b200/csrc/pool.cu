@@ -114,6 +114,7 @@ hd_status hd_pool_create(const hd_config *cfg, int device, hd_pool **out) {
 	p->cfg = *cfg;
 	p->geo = g;
 	p->device = device;
+	cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
 	cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess)
 		e = cudaMalloc(&p->words, g.total_words * sizeof(uint32_t));
@@ -162,6 +163,8 @@ void hd_pool_destroy(hd_pool *p) {
 	cudaFree(p->color_nodes);
 	cudaFree(p->color_leaves);
 	cudaFree(p->color_ctr);
+	cudaFree(p->color_dirty_list);
+	cudaFree(p->color_dirty_ctr);
 	cudaFree(p->stage_rgba);
 	cudaFree(p->stage_iters);
 	cudaFree(p->stage_fetches);

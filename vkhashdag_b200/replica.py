@@ -39,6 +39,18 @@ def assemble_frame(parts, width, height, tile_w, tile_h, world, dtype=None):
     return frame
 
 
+HEADER_BYTES = 32
+
+
+def packed_bytes(head):
+    """Size in bytes of a packed blob, from its 8-word header (the layout is documented in sync.cu)."""
+    h = [int(x) for x in head[:8]]
+    words = 8 + 3 * h[0] + h[1]
+    if h[3] & 2:   # colour section: two totals, its triples, its payload
+        words += 2 + 3 * h[4] + h[5]
+    return 4 * words
+
+
 class StagingTooSmall(Exception):
     """DirtyPack could not fit the packed dirty ranges; `.need` is the size in bytes that would."""
 
@@ -58,7 +70,7 @@ class ReplicaSync:
 
     def __init__(self, pool, dist, device, capacity_bytes=64 << 20, eager_bytes=256 << 10):
         self.pool, self.dist, self.device = pool, dist, device
-        self.eager = max(16, min(int(eager_bytes), int(capacity_bytes)) & ~3)
+        self.eager = max(HEADER_BYTES, min(int(eager_bytes), int(capacity_bytes)) & ~3)
         self.staging = torch.empty(max(int(capacity_bytes), self.eager), dtype=torch.uint8, device=device)
         self.collectives = 0   # payload collectives issued so far (tests / benches)
 
@@ -92,8 +104,7 @@ class ReplicaSync:
         self.dist.broadcast(self.staging[:self.eager], src)   # header + (normally) the whole payload
         self.collectives += 1
         if rank != src:
-            head = self.staging[:16].view(torch.int32).cpu().numpy().view("uint32")
-            n = 4 * (4 + 3 * int(head[0]) + int(head[1]))
+            n = packed_bytes(self.staging[:HEADER_BYTES].view(torch.int32).cpu().numpy().view("uint32"))
         if n > self.eager:                                     # large payload: one more broadcast for the remainder
             self._grow(n, keep=self.eager)
             self.dist.broadcast(self.staging[self.eager:n], src)
