@@ -164,6 +164,19 @@ void *hd_pool_stream(hd_pool *pool); /* cudaStream_t all pool work is enqueued o
  * DAGNodePool::Flush (src/DAGNodePool.cpp:56-85). */
 hd_status hd_pool_upload_words(hd_pool *pool, uint32_t word_offset, const uint32_t *src, uint32_t count);
 hd_status hd_pool_read_words(hd_pool *pool, uint32_t word_offset, uint32_t *dst, uint32_t count);
+/* One node as the host sees it after read_node/unpack (NodePool.hpp:264-317): inner = [mask, present children...]
+ * (n_words = 1 + popcount), leaf = the two voxel words (n_words = 2). */
+typedef struct hd_node_record {
+	uint32_t ptr, level, n_words;
+	uint32_t words[9];
+} hd_node_record;
+/* Breadth-first read-back of the subtree under `root` (a node of `level`), at most `depth` levels deep, in ONE device
+ * pass and one copy — what a host-side visitor such as NodePoolBase::Iterate (test/test.cpp:36-52,173-198) needs instead
+ * of one ReadPage round trip per node.  Records come level by level; a shared node appears once per parent that reaches it.
+ * *n_out = records written (<= capacity); HD_ERR_OVERFLOW when the subtree has more nodes than `capacity` (the
+ * records written are still valid, deeper nodes are missing). */
+hd_status hd_pool_read_subtree(hd_pool *pool, uint32_t root, uint32_t level, uint32_t depth, hd_node_record *out,
+                               uint32_t capacity, uint32_t *n_out);
 hd_status hd_pool_upload_bucket_words(hd_pool *pool, uint32_t first_bucket, const uint32_t *src, uint32_t count);
 hd_status hd_pool_read_bucket_words(hd_pool *pool, uint32_t first_bucket, uint32_t *dst, uint32_t count);
 /* m_filled_node_pointers (NodePool.hpp:54,240-262); made on first use like make_filled_node_pointers() */

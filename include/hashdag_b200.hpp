@@ -13,11 +13,14 @@
 #pragma once
 #include "hashdag_b200.h"
 
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <memory>
 #include <optional>
 #include <unordered_map>
+#include <utility>
+#include <variant>
 #include <vector>
 
 namespace hashdag_b200 {
@@ -118,8 +121,12 @@ enum class IterateType { kProceed, kStop };                    // test/test.cpp:
 enum class EditMode { kFill, kDig, kPaint };                   // main.cpp:72
 
 // ---- editors: the reference's structs reduced to their parameters (src/main.cpp:32-150) ----
+// `color` is the editor's hashdag::VBRColor as RGB8 (r in the low byte); it only matters when the editor is applied through
+// VBREditorWrapper (a colour-aware edit), exactly like in the reference.
 struct AABBEditor {
 	UVec3 aabb_min, aabb_max;
+	uint32_t color = 0;
+	static constexpr bool kPaint = false;
 	hd_edit_desc Desc() const {
 		hd_edit_desc d{};
 		d.kind = HD_EDIT_AABB_FILL;
@@ -129,19 +136,37 @@ struct AABBEditor {
 	}
 };
 template <EditMode Mode = EditMode::kFill> struct SphereEditor {
-	static_assert(Mode != EditMode::kPaint, "paint only edits colour: GPU colour edit is a 'next' row (SURVEY §8f N2)");
 	UVec3 center{};
 	uint64_t r2{};
+	uint32_t color = 0;
+	static constexpr bool kPaint = Mode == EditMode::kPaint;
+	static constexpr EditMode kMode = Mode;
 	hd_edit_desc Desc() const {
 		hd_edit_desc d{};
-		d.kind = Mode == EditMode::kDig ? HD_EDIT_SPHERE_DIG : HD_EDIT_SPHERE_FILL;
+		d.kind = Mode == EditMode::kDig ? HD_EDIT_SPHERE_DIG : HD_EDIT_SPHERE_FILL; // kPaint: the sphere shape, paint flag set by the wrapper
 		d.p0[0] = center.x, d.p0[1] = center.y, d.p0[2] = center.z;
 		d.r2 = r2;
 		return d;
 	}
 };
+
+// Editor wrappers with the reference's names and NodeState members (Editor.hpp:42-57, VBREditor.hpp:26-36).  The state the
+// reference hands to on_edit_done(root, state) is the ROOT node's state: std::monostate for a stateless edit, the colour
+// octree pointer (`octree_node`) for a colour-aware one (src/main.cpp:214-238 builds its EditResult from exactly that).
+template <typename Editor_T> struct StatelessEditorWrapper {
+	Editor_T editor;
+	using NodeState = std::monostate;
+};
+struct VBRNodeState {
+	uint32_t octree_node = HD_COLOR_NULL; // DAGColorPool::Pointer of the new colour root (tag << 30 | data)
+};
+template <typename Editor_T> struct VBREditorWrapper {
+	Editor_T editor;
+	using NodeState = VBRNodeState;
+};
 struct TerrainEditor { // synthetic scene generator
 	uint32_t seed, base, first_cell_bits, octaves, first_amplitude, extent_bits;
+	static constexpr bool kPaint = false;
 	static TerrainEditor ForLevel(uint32_t voxel_level, uint32_t seed = 0x5EED, uint32_t octaves = 4, uint32_t amp_div = 8,
 	                              uint32_t extent_bits = 0) {
 		const uint32_t bits = extent_bits ? extent_bits : voxel_level, ext = 1u << bits;
@@ -190,9 +215,28 @@ public:
 
 	// NodePoolBase::Edit (NodePool.hpp:405-417).  On any failure the old root is returned (the reference's
 	// silent-fallback convention); GetLastStatus()/GetLastEditStats().overflow_count tell why.
+	// A bare editor is applied statelessly (the reference's stateless_edit, main.cpp:231-234); VBREditorWrapper{editor}
+	// makes it the colour-aware vbr_edit (main.cpp:224-230); on_edit_done receives (new root, root NodeState).
 	template <typename Editor_T> NodePointer<uint32_t> Edit(NodePointer<uint32_t> root, const Editor_T &editor) {
+		return Edit(root, editor, [](NodePointer<uint32_t> r, auto &&) { return r; });
+	}
+	template <typename Editor_T, typename OnDone>
+	auto Edit(NodePointer<uint32_t> root, const StatelessEditorWrapper<Editor_T> &w, OnDone &&on_edit_done) {
+		return Edit(root, w.editor, std::forward<OnDone>(on_edit_done));
+	}
+	template <typename Editor_T, typename OnDone>
+	auto Edit(NodePointer<uint32_t> root, const VBREditorWrapper<Editor_T> &w, OnDone &&on_edit_done) {
+		VBRNodeState state{GetColorRoot()};
+		NodePointer<uint32_t> out = EditColor(root, w.editor, w.editor.color, Editor_T::kPaint);
+		if (m_last_status == HD_OK)
+			state.octree_node = GetColorRoot();
+		return on_edit_done(out, std::move(state));
+	}
+	template <typename Editor_T, typename OnDone> auto Edit(NodePointer<uint32_t> root, const Editor_T &editor, OnDone &&on_edit_done) {
+		static_assert(!Editor_T::kPaint, "SphereEditor<kPaint> only edits colour: apply it through VBREditorWrapper "
+		                                 "(the reference only ever calls it via vbr_edit, src/main.cpp:267-271)");
 		hd_edit_desc d = editor.Desc();
-		return EditBatch(root, &d, 1);
+		return on_edit_done(EditBatch(root, &d, 1), std::monostate{});
 	}
 	// NodePoolThreadedEdit::ThreadedEdit (NodePoolThreadedEdit.hpp:104-126).  The thread pool and task level are
 	// accepted for source compatibility and ignored: the GPU pass has its own scheduling.
@@ -202,8 +246,8 @@ public:
 		return Edit(root, editor);
 	}
 	template <typename Editor_T, typename OnDone>
-	auto ThreadedEdit(void *pool, NodePointer<uint32_t> root, const Editor_T &editor, uint32_t level, OnDone &&on_done) {
-		return on_done(ThreadedEdit(pool, root, editor, level));
+	auto ThreadedEdit(void *, NodePointer<uint32_t> root, const Editor_T &editor, uint32_t /*max_task_level*/, OnDone &&on_edit_done) {
+		return Edit(root, editor, std::forward<OnDone>(on_edit_done));
 	}
 	// n edits applied in index order in ONE GPU pass
 	NodePointer<uint32_t> EditBatch(NodePointer<uint32_t> root, const hd_edit_desc *edits, uint32_t n) {
@@ -228,12 +272,14 @@ public:
 
 	// Iterate, reconstructed from its only surviving use (test/test.cpp:36-52,173-198): IterateNode(coord, node) ->
 	// kProceed/kStop for every visited node, IterateVoxel(coord, bool) for all 64 voxels of every reached leaf at
-	// voxel-level coordinates; a Null root iterates nothing.  Nodes are read back on demand.
+	// voxel-level coordinates; a Null root iterates nothing.  Callbacks run depth first in child order like the
+	// reference's recursion; nodes come back from the device a SUBTREE at a time (hd_pool_read_subtree: kIterateDepth
+	// levels under the first node that is not cached yet), not one copy per node.
+	static constexpr uint32_t kIterateDepth = 5, kIterateCapacity = 1u << 16;
 	template <typename Iterator_T> void Iterate(NodePointer<uint32_t> root, Iterator_T *p_iterator) const {
-		std::unordered_map<uint32_t, std::array<uint32_t, 9>> cache;
+		NodeCache cache;
 		iterate_node(root, NodeCoord<uint32_t>{}, p_iterator, cache);
 	}
-
 	// NodePoolThreadedGC::ThreadedGC (NodePoolThreadedGC.hpp:394-403): compacts the pool on the GPU, returns the
 	// relocated root(s).  The thread pool argument is accepted for source compatibility and ignored.
 	NodePointer<uint32_t> ThreadedGC(void * /*lf::busy_pool* */, NodePointer<uint32_t> root) {
@@ -289,32 +335,35 @@ public:
 	}
 
 private:
-	const std::array<uint32_t, 9> &read_node(uint32_t ptr, uint32_t words,
-	                                         std::unordered_map<uint32_t, std::array<uint32_t, 9>> &cache) const {
+	using NodeCache = std::unordered_map<uint32_t, std::array<uint32_t, 9>>;
+	const std::array<uint32_t, 9> &read_node(uint32_t ptr, uint32_t level, NodeCache &cache) const {
 		auto it = cache.find(ptr);
 		if (it != cache.end())
 			return it->second;
-		std::array<uint32_t, 9> w{};
-		hd_pool_read_words(m_pool, ptr, w.data(), words);
-		return cache.emplace(ptr, w).first->second;
+		if (cache.size() > (1u << 20)) // bound the host copy on huge trees; what is dropped is simply read again
+			cache.clear();
+		std::vector<hd_node_record> rec(kIterateCapacity);
+		uint32_t n = 0;
+		hd_pool_read_subtree(m_pool, ptr, level, kIterateDepth, rec.data(), kIterateCapacity, &n); // truncated is fine
+		for (uint32_t i = 0; i < n; ++i) {
+			std::array<uint32_t, 9> w{};
+			std::copy(rec[i].words, rec[i].words + 9, w.begin());
+			cache.emplace(rec[i].ptr, w);
+		}
+		return cache.at(ptr);
 	}
 	template <typename Iterator_T>
-	void iterate_node(NodePointer<uint32_t> node, NodeCoord<uint32_t> coord, Iterator_T *it,
-	                  std::unordered_map<uint32_t, std::array<uint32_t, 9>> &cache) const {
+	void iterate_node(NodePointer<uint32_t> node, NodeCoord<uint32_t> coord, Iterator_T *it, NodeCache &cache) const {
 		if (it->IterateNode(coord, node) == IterateType::kStop || !node)
 			return;
 		if (coord.level == m_config.GetNodeLevels() - 1) {
-			const auto &leaf = read_node(*node, 2, cache);
+			const std::array<uint32_t, 9> leaf = read_node(*node, coord.level, cache);
 			for (uint32_t i = 0; i < 64; ++i)
 				it->IterateVoxel(coord.GetLeafCoord(i), (leaf[i >> 5] >> (i & 31u)) & 1u);
 			return;
 		}
-		const uint32_t mask = read_node(*node, 1, cache)[0] & 0xFFu;
-		uint32_t n = 1;
-		for (uint32_t m = mask; m; m &= m - 1)
-			++n;
-		cache.erase(*node);
-		const std::array<uint32_t, 9> w = read_node(*node, n, cache);
+		const std::array<uint32_t, 9> w = read_node(*node, coord.level, cache); // by value: the cache may be rebuilt below
+		const uint32_t mask = w[0] & 0xFFu;
 		uint32_t k = 1;
 		for (uint32_t i = 0; i < 8; ++i) {
 			NodePointer<uint32_t> child = (mask >> i & 1u) ? NodePointer<uint32_t>{w[k++]} : NodePointer<uint32_t>::Null();

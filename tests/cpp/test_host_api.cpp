@@ -127,6 +127,38 @@ int main() {
 		auto hit4 = loaded->Traversal<float>(loaded->GetRoot(), {0.5f, 0.5f, 1.5f}, {0.f, 0.f, -1.f});
 		CHECK(hit4 && hit4->z == hit2->z);
 	}
+	{ // colour-aware edits with the reference's wrapper names and its on_edit_done(root, state) contract (main.cpp:214-279)
+		auto pool = DAGNodePool::Create(DefaultConfig<uint32_t>{.level_count = 8, .top_level_count = 9}());
+		CHECK(pool && pool->ConfigureColor(4));
+		struct EditResult {
+			NodePointer<uint32_t> node_ptr;
+			std::optional<uint32_t> opt_color_ptr;
+		};
+		const auto edit = [&](auto &&editor) -> EditResult {
+			return pool->ThreadedEdit(nullptr, pool->GetRoot(), editor, 4, [&](NodePointer<uint32_t> root_ptr, auto &&state) -> EditResult {
+				if constexpr (requires { state.octree_node; })
+					return {root_ptr, state.octree_node};
+				else
+					return {root_ptr, std::nullopt};
+			});
+		};
+		auto r1 = edit(VBREditorWrapper<AABBEditor>{{{10, 10, 10}, {100, 60, 100}, 0xFFFFFF}});
+		CHECK(r1.node_ptr && r1.opt_color_ptr && *r1.opt_color_ptr == pool->GetColorRoot() && pool->GetLastStatus() == HD_OK);
+		pool->SetRoot(r1.node_ptr);
+		auto r2 = edit(VBREditorWrapper<SphereEditor<EditMode::kPaint>>{{{50, 40, 50}, 900, 0x007FFF}});
+		CHECK(r2.node_ptr == r1.node_ptr);                                        // paint leaves the geometry alone
+		CHECK(r2.opt_color_ptr && *r2.opt_color_ptr != *r1.opt_color_ptr);        // ... and changes the colour octree
+		auto r3 = edit(StatelessEditorWrapper<SphereEditor<EditMode::kDig>>{{{50, 60, 50}, 400}});
+		CHECK(!r3.opt_color_ptr && r3.node_ptr && r3.node_ptr != r2.node_ptr);    // stateless: no colour state
+		auto r4 = edit(SphereEditor<EditMode::kFill>{{30, 30, 30}, 100});          // a bare editor is stateless too
+		CHECK(!r4.opt_color_ptr && r4.node_ptr);
+		// Iterate over a tree of a few thousand nodes: whole subtrees come back per device round trip
+		CountIterator cnt;
+		const uint64_t launches0 = hd_kernel_launches();
+		pool->Iterate(r1.node_ptr, &cnt);
+		CHECK(cnt.voxels == 90ull * 50 * 90);
+		CHECK(hd_kernel_launches() - launches0 < 2000);                           // far fewer read-backs than nodes
+	}
 	std::puts("cpp host api: OK");
 	return 0;
 }

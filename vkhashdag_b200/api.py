@@ -39,6 +39,10 @@ class HdTileShard(C.Structure):
     _fields_ = [("tile_w", C.c_uint32), ("tile_h", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32)]
 
 
+class HdNodeRecord(C.Structure):
+    _fields_ = [("ptr", C.c_uint32), ("level", C.c_uint32), ("n_words", C.c_uint32), ("words", C.c_uint32 * 9)]
+
+
 class HdDirtyRange(C.Structure):
     _fields_ = [("word_offset", C.c_uint32), ("word_count", C.c_uint32)]
 
@@ -64,7 +68,7 @@ SYMBOLS = [
     "hd_pool_load", "hd_gc", "hd_trace_submit", "hd_trace_collect", "hd_beam_dev",
     "hd_trace_with_beam_dev", "hd_trace_with_beam", "hd_color_config", "hd_color_root", "hd_color_leaf_level",
     "hd_color_sizes", "hd_color_read", "hd_edit_color", "hd_edit_last_path",
-    "hd_tile_shard_locate",
+    "hd_tile_shard_locate", "hd_pool_read_subtree",
 ]
 
 
@@ -102,6 +106,7 @@ def lib():
         getattr(L, f).argtypes = [vp]
     L.hd_pool_upload_words.argtypes = [vp, u32, vp, u32]
     L.hd_pool_read_words.argtypes = [vp, u32, vp, u32]
+    L.hd_pool_read_subtree.argtypes = [vp, u32, u32, u32, C.POINTER(HdNodeRecord), u32, pu32]
     L.hd_pool_upload_bucket_words.argtypes = [vp, u32, vp, u32]
     L.hd_pool_read_bucket_words.argtypes = [vp, u32, vp, u32]
     L.hd_pool_filled_nodes.argtypes = [vp, pu32]
@@ -295,6 +300,15 @@ class DAGNodePool:
         out = np.empty(count, np.uint32)
         _check(self._L.hd_pool_read_words(self._h, word_offset, out.ctypes.data, count))
         return out
+
+    def ReadSubtree(self, root, level=0, depth=64, capacity=1 << 16):
+        """hd_pool_read_subtree: [(ptr, level, [words])] of the subtree under `root`, breadth first, one device pass."""
+        arr = (HdNodeRecord * capacity)()
+        n = C.c_uint32()
+        st = self._L.hd_pool_read_subtree(self._h, root, level, depth, arr, capacity, C.byref(n))
+        if st not in (HD_OK, HD_ERR_OVERFLOW):
+            _check(st)
+        return [(r.ptr, r.level, list(r.words[:r.n_words])) for r in arr[:n.value]], st == HD_ERR_OVERFLOW
 
     def UploadBucketWords(self, first_bucket, values):
         a = np.ascontiguousarray(values, dtype=np.uint32)

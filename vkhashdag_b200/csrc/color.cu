@@ -634,20 +634,35 @@ hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, 
 	hd_status st = ensure_color_storage(p, p->color_node_words, p->color_leaf_words);
 	if (st != HD_OK)
 		return st;
+	// ---- geometry first (SphereEditor<kPaint> leaves the voxels alone, main.cpp:133-136): the node pool is append-only, so
+	// a failure here (bucket overflow, CUDA error) leaves both pools exactly as they were, and the colour pass below still
+	// sees the OLD geometry under root_in.  Only the in-place rewrite of leaf chunks cannot be rolled back once it starts.
+	uint32_t new_root = root_in;
+	if (!paint) {
+		st = hd_edit_batch(p, root_in, edit, 1, &new_root, stats);
+		if (st != HD_OK)
+			return st;
+	} else if (stats)
+		memset(stats, 0, sizeof(*stats));
 
-	// ---- colour pass over the OLD geometry (node memory is immutable, so the order w.r.t. the geometry edit is free) ----
+	// ---- colour pass over the OLD geometry (node memory is immutable) ----
 	std::vector<CLevel> inner(LL + 1);
 	CLevel leaf;
 	uint32_t *counts = nullptr, *root_dev = nullptr; // counts: [inner created, leaves created, -, overflow]
 	HD_CUDA_TRY(cmalloc(&counts, 4, s));
 	HD_CUDA_TRY(cmalloc(&root_dev, 1, s));
+	bool cleaned = false;
 	auto cleanup = [&]() {
+		if (cleaned)
+			return;
+		cleaned = true;
 		for (auto &l : inner)
 			l.release();
 		leaf.release();
 		cudaFreeAsync(counts, s), cudaFreeAsync(root_dev, s);
 		cudaStreamSynchronize(s);
 	};
+	ScopeExit guard{cleanup}; // the HD_CUDA_TRY early returns below release the stream-ordered scratch as well
 	uint32_t hc[4] = {0, 0, 0, 0};
 	auto read_counts = [&]() -> hd_status {
 		HD_CUDA_TRY(cudaMemcpyAsync(hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, s));
@@ -791,13 +806,7 @@ hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, 
 	p->color_dirty = true;
 	*color_root_out = new_color_root;
 
-	// ---- geometry (SphereEditor<kPaint> leaves the voxels alone, main.cpp:133-136) ----
-	if (!paint) {
-		st = hd_edit_batch(p, root_in, edit, 1, root_out, stats);
-		if (st != HD_OK)
-			return st;
-	} else if (stats)
-		memset(stats, 0, sizeof(*stats));
+	*root_out = new_root;
 	if (stats)
 		stats->in_range_voxels = leaf_voxels; // colour voxels re-encoded (diagnostic)
 	return HD_OK;

@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -32,6 +33,15 @@ extern std::atomic<uint64_t> g_launches;
 		hd::g_launches.fetch_add(1, std::memory_order_relaxed);                                                        \
 		HD_CUDA_TRY(cudaGetLastError());                                                                               \
 	} while (0)
+
+// runs `f` on every exit path of the enclosing scope (the early returns of HD_CUDA_TRY included)
+struct ScopeExit {
+	std::function<void()> f;
+	~ScopeExit() {
+		if (f)
+			f();
+	}
+};
 
 // ---- pool geometry (include/hashdag/Config.hpp:15-57), passed to kernels by value -----------------
 struct Geometry {

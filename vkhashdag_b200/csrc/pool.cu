@@ -51,6 +51,52 @@ bool make_geometry(const hd_config &cfg, Geometry &g) {
 
 using namespace hd;
 
+namespace hd {
+// hd_pool_read_subtree: one CTA walks the subtree level by level; the records of a level are the frontier of the next.
+__global__ void __launch_bounds__(256) k_read_subtree(const uint32_t *__restrict__ words, uint32_t node_levels, uint32_t root,
+                                                      uint32_t level, uint32_t depth, hd_node_record *out, uint32_t capacity,
+                                                      uint32_t *n_out /* [0] = records, [1] = truncated */) {
+	__shared__ uint32_t s_begin, s_end, s_next;
+	if (threadIdx.x == 0) {
+		s_begin = 0, s_end = 1, s_next = 1;
+		out[0].ptr = root, out[0].level = level;
+		n_out[1] = 0;
+	}
+	__syncthreads();
+	for (uint32_t d = 0;; ++d) {
+		const uint32_t begin = s_begin, end = s_end;
+		for (uint32_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+			hd_node_record &r = out[i];
+			const bool leaf = r.level == node_levels - 1u;
+			const uint32_t first = words[r.ptr];
+			const uint32_t n = leaf ? 2u : 1u + __popc(first & 0xFFu);
+			r.n_words = n;
+			r.words[0] = first;
+			for (uint32_t k = 1; k < n; ++k)
+				r.words[k] = words[r.ptr + k];
+			for (uint32_t k = n; k < 9u; ++k)
+				r.words[k] = 0u;
+			if (!leaf && d + 1 < depth) {
+				const uint32_t slot = atomicAdd(&s_next, n - 1u);
+				for (uint32_t k = 1; k < n; ++k)
+					if (slot + k - 1u < capacity)
+						out[slot + k - 1u].ptr = r.words[k], out[slot + k - 1u].level = r.level + 1u;
+					else
+						n_out[1] = 1u;
+			}
+		}
+		__syncthreads();
+		if (threadIdx.x == 0)
+			s_begin = end, s_end = min(s_next, capacity), s_next = min(s_next, capacity);
+		__syncthreads();
+		if (s_begin == s_end)
+			break;
+	}
+	if (threadIdx.x == 0)
+		n_out[0] = s_end;
+}
+} // namespace hd
+
 extern "C" {
 
 const char *hd_version(void) { return "hashdag_b200 0.1 (sm_100a)"; }
@@ -231,6 +277,39 @@ hd_status hd_pool_read_words(hd_pool *p, uint32_t off, uint32_t *dst, uint32_t c
 	HD_CUDA_TRY(cudaSetDevice(p->device));
 	HD_CUDA_TRY(cudaMemcpyAsync(dst, p->words + off, size_t(count) * 4, cudaMemcpyDeviceToHost, p->stream));
 	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	return HD_OK;
+}
+hd_status hd_pool_read_subtree(hd_pool *p, uint32_t root, uint32_t level, uint32_t depth, hd_node_record *out, uint32_t capacity,
+                               uint32_t *n_out) {
+	if (!p || !out || !n_out || capacity == 0 || depth == 0 || level >= p->geo.node_levels)
+		return HD_ERR_INVALID;
+	*n_out = 0;
+	if (root == HD_NULL_NODE)
+		return HD_OK;
+	if (uint64_t(root) + 2 > p->geo.total_words)
+		return HD_ERR_INVALID;
+	HD_CUDA_TRY(cudaSetDevice(p->device));
+	hd_node_record *dev = nullptr;
+	uint32_t *cnt = nullptr, h[2] = {0, 0};
+	ScopeExit guard{[&]() {
+		if (dev)
+			cudaFreeAsync(dev, p->stream);
+		if (cnt)
+			cudaFreeAsync(cnt, p->stream);
+	}};
+	HD_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&dev), size_t(capacity) * sizeof(hd_node_record), p->stream));
+	HD_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&cnt), 8, p->stream));
+	k_read_subtree<<<1, 256, 0, p->stream>>>(p->words, p->geo.node_levels, root, level, depth, dev, capacity, cnt);
+	HD_LAUNCH_CHECK();
+	HD_CUDA_TRY(cudaMemcpyAsync(h, cnt, 8, cudaMemcpyDeviceToHost, p->stream));
+	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	HD_CUDA_TRY(cudaMemcpyAsync(out, dev, size_t(h[0]) * sizeof(hd_node_record), cudaMemcpyDeviceToHost, p->stream));
+	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	*n_out = h[0];
+	if (h[1]) {
+		set_error("hd_pool_read_subtree: more than %u nodes, the deepest levels are missing", capacity);
+		return HD_ERR_OVERFLOW;
+	}
 	return HD_OK;
 }
 hd_status hd_pool_upload_bucket_words(hd_pool *p, uint32_t first, const uint32_t *src, uint32_t count) {

@@ -428,6 +428,7 @@ hd_status hd_pool_save(hd_pool *p, const char *path) {
 	HD_CUDA_TRY(cudaSetDevice(p->device));
 	const uint32_t nb = p->geo.total_buckets;
 	uint32_t *zeros = nullptr, *stg = nullptr;
+	ScopeExit guard{[&]() { cudaFree(zeros), cudaFree(stg); }};
 	HD_CUDA_TRY(cudaMalloc(&zeros, size_t(nb) * 4));
 	HD_CUDA_TRY(cudaMemsetAsync(zeros, 0, size_t(nb) * 4, p->stream));
 	hd_status s = ensure_dirty_scratch(p, kHeaderWords * 4);
@@ -450,15 +451,19 @@ hd_status hd_pool_save(hd_pool *p, const char *path) {
 		k_dirty_gather<<<std::min<uint32_t>(h[0], 148u * 8u), 256, 0, p->stream>>>(p->words, stg, uint32_t(blob / 4));
 		HD_LAUNCH_CHECK();
 	}
-	std::vector<uint32_t> host(blob / 4);
+	std::vector<uint32_t> host, cn, cl;
+	try {
+		host.resize(blob / 4), cn.resize(p->color_node_words), cl.resize(p->color_leaf_words);
+	} catch (...) { // nothing may throw through the C ABI
+		set_error("pool save: out of host memory");
+		return HD_ERR_OOM;
+	}
 	HD_CUDA_TRY(cudaMemcpyAsync(host.data(), stg, blob, cudaMemcpyDeviceToHost, p->stream));
-	std::vector<uint32_t> cn(p->color_node_words), cl(p->color_leaf_words);
 	if (!cn.empty())
 		HD_CUDA_TRY(cudaMemcpyAsync(cn.data(), p->color_nodes, cn.size() * 4, cudaMemcpyDeviceToHost, p->stream));
 	if (!cl.empty())
 		HD_CUDA_TRY(cudaMemcpyAsync(cl.data(), p->color_leaves, cl.size() * 4, cudaMemcpyDeviceToHost, p->stream));
 	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
-	cudaFree(zeros), cudaFree(stg);
 	host[2] = p->root;
 	FileHeader fh{};
 	memcpy(fh.magic, "HDAGB200", 8);
