@@ -54,7 +54,7 @@ EDIT_BATCH = 10000        # sphere edits of BASELINE.json config 3
 # The largest square power-of-two patch that fits is therefore 2^16 (1/4 of the world's area): 3.64 G words of address
 # space with the per-level bucket bits below (level 14 at 2^20 buckets is 25 % full after the terrain).
 CFG3_PATCH_BITS = 16
-CFG3_BUCKET_BITS = [10] * 9 + [16, 16, 16, 17, 18, 20, 17]
+CFG3_BUCKET_BITS = [10] * 9 + [16, 16, 16, 17, 18, 19, 17]
 
 
 def scene_config():

@@ -86,6 +86,18 @@ def test_random_sphere_batch(oracle, hd):
     check_equal(oracle, hd, cfg, edits)[0].close()
 
 
+def test_random_sphere_batch_general_path(oracle, hd):
+    """More than 1024 editors: the host-driven level-synchronous path with the fused last-level + leaf kernel
+    (k_down_leaf), batch dedup and the bucket-grouped find-or-insert."""
+    cfg = abi.default_config(level_count=9, top_level_count=9)
+    edits = abi.random_spheres(1100, cfg.voxel_level, seed=7, rmin=3, rmax=24, y_lo=60, y_hi=450)
+    dev = check_equal(oracle, hd, cfg, edits)[0]
+    assert dev.last_stats["path"] == "general" and dev.last_stats["visited_leaves"] > 100000
+    dev.close()
+    # the same list as two batches on top of each other (the second one edits an existing scene)
+    check_equal(oracle, hd, cfg, edits, batches=[1050, 50])[0].close()
+
+
 def test_terrain_and_spheres(oracle, hd):
     cfg = abi.default_config(level_count=9, top_level_count=9)
     vl = cfg.voxel_level
@@ -260,8 +272,8 @@ def test_low_latency_queue_overflow_falls_back(oracle, hd):
 
 
 def test_degenerate_edits(oracle, hd):
-    """Edge cases of the editor contract on the GPU paths (one call per edit -> low-latency path; one batch; and a batch
-    padded past 32 editors -> general path): single-voxel and zero-volume edits, edits clipped by or outside the world,
+    """Edge cases of the editor contract on the GPU paths (one call per edit -> low-latency path; one batch; a batch padded
+    past 32 editors -> long lists on the low-latency path; and one padded past 1024 editors -> general path): single-voxel and zero-volume edits, edits clipped by or outside the world,
     whole-world fill and clear, digging in empty space, repeated edits."""
     cfg = abi.default_config(level_count=6, top_level_count=9)
     res = 1 << cfg.voxel_level
@@ -273,7 +285,11 @@ def test_degenerate_edits(oracle, hd):
     ]
     check_equal(oracle, hd, cfg, edits, batches=[1] * len(edits))[0].close()
     check_equal(oracle, hd, cfg, edits)[0].close()
-    padded = edits + [abi.sphere((20, 20, 20), 4, dig=True)] * 30      # 39 editors: the general path
+    padded = edits + [abi.sphere((20, 20, 20), 4, dig=True)] * 30      # 39 editors: lists longer than 32 on the one-launch path
+    dev = check_equal(oracle, hd, cfg, padded)[0]
+    assert dev.last_stats["path"] in ("fused", "graph")
+    dev.close()
+    padded = edits + [abi.sphere((20, 20, 20), 4, dig=True)] * 1030    # past the one-launch path's 1024 editors: general path
     dev = check_equal(oracle, hd, cfg, padded)[0]
     assert dev.last_stats["path"] == "general"
     dev.close()

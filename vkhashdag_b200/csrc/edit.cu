@@ -83,7 +83,8 @@ struct LevelView {
 // CUDA graph.  A call costs one graph launch and one 16-byte-aligned counter read-back instead of ~2 host round trips
 // per level.  A queue that turns out too small sets DevCounters::error before anything touches the pool (k_upsert
 // checks it), and the call falls back to the exactly-sized general path.
-constexpr uint32_t kFastMaxEdits = 32; // lists never exceed 32 entries -> k_down_long is never needed
+constexpr uint32_t kFastMaxEdits = 1024; // batches up to this many editors take the one-launch path; lists longer than 32
+                                         // entries (only near the root) are filtered serially by the child's thread there
 struct FastDyn {
 	uint32_t root, n_edits, pad[2];
 	hd_edit_desc edits[kFastMaxEdits];
@@ -449,13 +450,15 @@ __device__ __forceinline__ void phase_down(const Geometry &g, uint32_t level /* 
 			x = (x << 1) | (c & 1u), y = (y << 1) | ((c >> 1) & 1u), z = (z << 1) | ((c >> 2) & 1u); // NodeCoord.hpp:18-28
 			list = in.lists + in.list_off[item];
 			len = in.list_len[item];
-			if (len <= 32u)
+			// lists longer than 32: k_down_long on the host-driven path; on the one-launch path (device-resident counts)
+			// this thread walks them itself — they only occur in the few levels next to the root
+			if (len <= 32u || in.n_dev)
 				f = filter_list<kTerrain>(edits, list, len, bits, x, y, z, child, filled[level + 1u]);
 		}
 		uint32_t slot, entry_off;
 		const bool made = alloc_item(ctr, items_ctr, entries_ctr, valid && f.count != 0, f.count, out.cap, out.cap_entries,
 		                             slot, entry_off, s_alloc);
-		if (!valid || len > 32u)
+		if (!valid || (len > 32u && !in.n_dev))
 			continue; // long lists: k_down_long
 		if (made) {
 			out.cur[slot] = f.cur;
@@ -598,6 +601,159 @@ __global__ void __launch_bounds__(kBlock, 5) k_leaf_half(Geometry g, const uint3
 			lv.state[mine] = o_st;
 			lv.result[mine] = o_res;
 		}
+	}
+}
+
+// Leaf pass, ONE THREAD PER LEAF (batches without a terrain edit; HD_EDIT_LEAF=half brings k_leaf_half back).
+// The cooperative kernels above spend most of their 78 warp instructions per leaf on plumbing (record shuffles, coordinate
+// unpacking per lane, four ballots, the owner's re-assembly) and evaluate 4 voxels per lane; here a lane owns a whole
+// 4x4x4 leaf: its record loads are coalesced across the warp, nothing is exchanged between lanes, and a sphere edit
+// (EditVoxel, main.cpp:127-142) costs two instructions per voxel — the squares (dx+i)^2, (dy+j)^2, (dz+k)^2 are formed
+// once (12 multiplies, 16 sums), then per voxel one three-input add r2 - X[i] - YZ[j,k] whose SIGN is the "outside" flag
+// and one funnel shift that moves that sign bit into the 64-bit mask.  The 32-bit form is exact while every |d| < 26 000
+// (3 * 26 003^2 < 2^31; r2 is clamped to 2^31 - 1, beyond which every such voxel is inside anyway); farther from the
+// centre, and for AABBs, the voxels are evaluated one by one with the reference's 64-bit arithmetic.
+__device__ __forceinline__ void leaf_mask_generic(const hd_edit_desc &e, uint32_t bx, uint32_t by, uint32_t bz, uint32_t &in0,
+                                                  uint32_t &in1) {
+	in0 = in1 = 0u;
+	for (uint32_t i = 0; i < 64u; ++i) { // leaf bit i = [z1 y1 x1 z0 y0 x0] (NodeCoord.hpp:32-43)
+		const uint32_t vx = bx | ((i >> 2) & 2u) | (i & 1u), vy = by | ((i >> 3) & 2u) | ((i >> 1) & 1u),
+		               vz = bz | ((i >> 4) & 2u) | ((i >> 2) & 1u);
+		if (voxel_in_range<false>(e, vx, vy, vz)) {
+			if (i < 32u)
+				in0 |= 1u << i;
+			else
+				in1 |= 1u << (i - 32u);
+		}
+	}
+}
+// EditVoxel of one edit over all 64 voxels of the leaf at voxel origin (bx, by, bz): (n0, n1) in, (n0, n1) out.
+__device__ __forceinline__ void leaf_apply(const hd_edit_desc &e, uint32_t bx, uint32_t by, uint32_t bz, uint32_t &n0, uint32_t &n1) {
+	const uint2 k0 = *reinterpret_cast<const uint2 *>(&e.kind), k1 = *reinterpret_cast<const uint2 *>(&e.p0[1]);
+	const uint32_t kind = k0.x;
+	uint32_t in0, in1;
+	const int32_t dx = int32_t(bx - k0.y), dy = int32_t(by - k1.x), dz = int32_t(bz - k1.y);
+	const uint32_t far = max(max(uint32_t(abs(dx)), uint32_t(abs(dx + 3))),
+	                         max(max(uint32_t(abs(dy)), uint32_t(abs(dy + 3))), max(uint32_t(abs(dz)), uint32_t(abs(dz + 3)))));
+	if ((kind == HD_EDIT_SPHERE_FILL || kind == HD_EDIT_SPHERE_DIG) && far < 26000u) {
+		const uint64_t r2 = e.r2;
+		const int32_t r = int32_t(r2 > 0x7FFFFFFFull ? 0x7FFFFFFFu : uint32_t(r2));
+		int32_t X[4], YZ[16];
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			X[i] = (dx + i) * (dx + i);
+#pragma unroll
+		for (int a = 0; a < 4; ++a)
+#pragma unroll
+			for (int b = 0; b < 4; ++b)
+				YZ[a * 4 + b] = (dy + a) * (dy + a) + (dz + b) * (dz + b);
+		uint32_t m0 = 0u, m1 = 0u; // bit = 1: OUTSIDE (r2 - d^2 < 0)
+#pragma unroll
+		for (int i = 31; i >= 0; --i) {
+			const int xi = ((i >> 3) & 1) * 2 + (i & 1), yi = ((i >> 4) & 1) * 2 + ((i >> 1) & 1), zi = (i >> 2) & 1;
+			m0 = __funnelshift_l(uint32_t(r - X[xi] - YZ[yi * 4 + zi]), m0, 1);
+			m1 = __funnelshift_l(uint32_t(r - X[xi] - YZ[yi * 4 + zi + 2]), m1, 1);
+		}
+		in0 = ~m0, in1 = ~m1;
+	} else {
+		leaf_mask_generic(e, bx, by, bz, in0, in1);
+	}
+	if (kind == HD_EDIT_SPHERE_DIG)
+		n0 &= ~in0, n1 &= ~in1;
+	else
+		n0 |= in0, n1 |= in1;
+}
+
+__global__ void __launch_bounds__(kBlock) k_leaf_lane(Geometry g, const uint32_t *__restrict__ words,
+                                                      const hd_edit_desc *__restrict__ edits, LevelView lv, DevCounters *ctr) {
+	const uint32_t n = lv.count();
+	for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n; item += gridDim.x * blockDim.x) {
+		const uint32_t cur = lv.cur[item], len = lv.list_len[item];
+		const uint32_t *list = lv.lists + lv.list_off[item];
+		uint32_t x, y, z, w0 = 0u, w1 = 0u;
+		unpack_pos(lv.pos[item], x, y, z);
+		if (cur != kNull) {
+			const uint2 w = *reinterpret_cast<const uint2 *>(words + cur);
+			w0 = w.x, w1 = w.y;
+		}
+		uint32_t n0 = w0, n1 = w1;
+		for (uint32_t j = 0; j < len; ++j)
+			leaf_apply(edits[list[j]], x << 2, y << 2, z << 2, n0, n1);
+		uint32_t res = cur;
+		uint8_t st = 0;
+		if (n0 != w0 || n1 != w1) { // changed (edit_leaf tail, NodePool.hpp:336-342)
+			if ((n0 | n1) == 0u)
+				res = kNull;
+			else {
+				st = 1;
+				*reinterpret_cast<uint2 *>(lv.cand + size_t(item) * 2u) = make_uint2(n0, n1);
+			}
+		}
+		lv.state[item] = st;
+		lv.result[item] = res;
+	}
+}
+
+// Last inner level and the leaf pass in ONE kernel (batches without a terrain edit, lists of <= 32 entries): the thread
+// that classifies child c of an item of level L-2 (EditNode on the leaf's box, filter_list) goes on to apply the surviving
+// edits to that leaf itself (leaf_apply) instead of writing a 24-byte queue record plus list for k_leaf_lane to read back.
+// Only CHANGED, non-empty leaves get a slot in the (compact) leaf level that the find-or-insert then works on: the cfg3 batch
+// visits 138.6 M leaves and changes a tenth of them, so the dedup / bucket-sort / resolve kernels of the leaf level shrink
+// with it.  Unchanged and emptied leaves report straight into the parent's child_new.
+__global__ void __launch_bounds__(kBlock) k_down_leaf(Geometry g, const uint32_t *__restrict__ words,
+                                                      const hd_edit_desc *__restrict__ edits, const uint32_t *__restrict__ filled,
+                                                      LevelView in, LevelView out, DevCounters *ctr) {
+	__shared__ uint32_t s_alloc[2 * (kMaxWarps + 1)];
+	const uint32_t level = g.node_levels - 2u, n8 = in.count() * 8u, filled_leaf = filled[g.node_levels - 1u];
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t item = t >> 3, c = t & 7u;
+	const bool valid = t < n8;
+	bool evaluated = false, changed = false;
+	uint32_t n0 = 0u, n1 = 0u, base_ptr = kNull;
+	if (valid) {
+		const uint32_t cur = in.cur[item];
+		uint32_t child = kNull;
+		if (cur != kNull) {
+			const uint32_t mask = words[cur];
+			if (mask >> c & 1u)
+				child = words[cur + 1u + __popc(mask & ((1u << c) - 1u))];
+		}
+		uint32_t x, y, z;
+		unpack_pos(in.pos[item], x, y, z);
+		x = (x << 1) | (c & 1u), y = (y << 1) | ((c >> 1) & 1u), z = (z << 1) | ((c >> 2) & 1u);
+		const uint32_t *list = in.lists + in.list_off[item];
+		const uint32_t len = in.list_len[item];
+		const Filtered f = filter_list<false>(edits, list, len, g.voxel_level() - (level + 1u), x, y, z, child, filled_leaf);
+		base_ptr = f.cur;
+		if (f.count == 0u)
+			in.child_new[size_t(item) * 8u + c] = f.cur;
+		else {
+			evaluated = true;
+			uint32_t w0 = 0u, w1 = 0u;
+			if (f.cur != kNull) {
+				const uint2 w = *reinterpret_cast<const uint2 *>(words + f.cur);
+				w0 = w.x, w1 = w.y;
+			}
+			n0 = w0, n1 = w1;
+			for (uint32_t keep = f.keep; keep; keep &= keep - 1u)
+				leaf_apply(edits[list[__ffs(keep) - 1]], x << 2, y << 2, z << 2, n0, n1);
+			if (n0 == w0 && n1 == w1)
+				in.child_new[size_t(item) * 8u + c] = f.cur; // unchanged (edit_leaf tail, NodePool.hpp:336-342)
+			else if ((n0 | n1) == 0u)
+				in.child_new[size_t(item) * 8u + c] = kNull;
+			else
+				changed = true;
+		}
+	}
+	const uint32_t n_eval = __syncthreads_count(evaluated);
+	if (threadIdx.x == 0 && n_eval)
+		atomicAdd(&ctr->stats[1], (unsigned long long)n_eval);
+	uint32_t slot, entry_off;
+	if (alloc_item(ctr, &ctr->next_items, &ctr->next_entries, changed, 0u, out.cap, out.cap_entries, slot, entry_off, s_alloc)) {
+		out.cur[slot] = base_ptr; // the bucket-full fallback of upsert_leaf (NodePool.hpp:195)
+		out.parent[slot] = (item << 3) | c;
+		*reinterpret_cast<uint2 *>(out.cand + size_t(slot) * 2u) = make_uint2(n0, n1);
+		in.child_new[size_t(item) * 8u + c] = kPending;
 	}
 }
 
@@ -1090,7 +1246,10 @@ __global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_const
 	if (blockIdx.x == 0) {
 		for (uint32_t i = threadIdx.x; i < sizeof(DevCounters) / 4; i += blockDim.x)
 			reinterpret_cast<uint32_t *>(ctr)[i] = 0u;
-		for (uint32_t i = threadIdx.x; i < sizeof(FastDyn) / 4; i += blockDim.x)
+		// only the header and the descriptors in use cross PCIe (a brush call is 56 bytes, not the 40 KB the struct can hold)
+		const uint32_t n_words = 4u + min(reinterpret_cast<const volatile uint32_t *>(a.dyn_host)[1], kFastMaxEdits) *
+		                                  uint32_t(sizeof(hd_edit_desc) / 4);
+		for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x)
 			reinterpret_cast<uint32_t *>(a.dyn_dev)[i] = reinterpret_cast<const volatile uint32_t *>(a.dyn_host)[i];
 		__syncthreads();
 		if (threadIdx.x < 32)
@@ -1198,11 +1357,21 @@ struct LevelAlloc {
 		(void)leaf;
 		return cudaSuccess;
 	}
-	// arrays only needed once the item count is known
-	cudaError_t init_up(bool leaf) {
+	// the compact leaf level k_down_leaf fills: fallback pointer, parent slot and the new leaf words of CHANGED leaves only
+	cudaError_t init_compact_leaves(uint32_t cap, cudaStream_t stream) {
+		s = stream;
+		v.cap = cap, v.cap_entries = 0, v.n = 0;
 		cudaError_t e;
-		if ((e = amalloc(&v.result, v.n, s)) || (e = amalloc(&v.state, v.n, s)) || (e = amalloc(&v.winner, v.n, s)) ||
-		    (e = amalloc(&v.cand, uint64_t(v.n) * (leaf ? 2 : 9), s)))
+		if ((e = amalloc(&v.cur, cap, s)) || (e = amalloc(&v.parent, cap, s)) || (e = amalloc(&v.cand, uint64_t(cap) * 2, s)))
+			return e;
+		return cudaSuccess;
+	}
+	// arrays only needed once the item count is known
+	cudaError_t init_up(bool leaf, bool with_cand = true) {
+		cudaError_t e;
+		if ((e = amalloc(&v.result, v.n, s)) || (e = amalloc(&v.state, v.n, s)) || (e = amalloc(&v.winner, v.n, s)))
+			return e;
+		if (with_cand && (e = amalloc(&v.cand, uint64_t(v.n) * (leaf ? 2 : 9), s)))
 			return e;
 		if (!leaf && (e = amalloc(&v.child_new, uint64_t(v.n) * 8, s)))
 			return e;
@@ -1324,14 +1493,28 @@ __global__ void __launch_bounds__(kGroupThreads) k_upsert_grouped(Geometry g, ui
 	const uint32_t bucket = g.level_base[level] + b, base = bucket << g.bucket_shift();
 	const uint32_t bw = bucket_words[bucket], wpp = g.words_per_page(), wpb = g.words_per_bucket();
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-	uint32_t *tab = img + wpb; // open-addressing index over the image: 0 = empty, else node position + 1 (wpb slots, <= 50 % full)
-	const uint32_t tmask = wpb - 1u;
+	// open-addressing index over the image: 0 = empty, else node position + 1.  Only stored nodes are indexed (at most bw / 2
+	// of them), so the table is the next power of two >= bw slots (<= 50 % full) instead of always wpb: with 2^20 buckets at
+	// the 8^3-node level of the cfg3 batch a bucket holds ~600 words and a dozen candidates, and zeroing 2 048 slots word by
+	// word was the longest phase of the CTA.  Staging and zeroing move 16 bytes per thread (the bucket base is 8 KB-aligned
+	// and everything behind bw is zero).
+	uint32_t *tab = img + wpb;
+	uint32_t tsize = 64u;
+	while (tsize < bw)
+		tsize <<= 1;
+	const uint32_t tmask = tsize - 1u;
 	const bool indexed = is_leaf || fast_scan;
-	for (uint32_t i = threadIdx.x; i < bw; i += kGroupThreads)
-		img[i] = words[base + i];
-	if (indexed)
-		for (uint32_t i = threadIdx.x; i < wpb; i += kGroupThreads)
-			tab[i] = 0u;
+	{
+		const uint4 *src = reinterpret_cast<const uint4 *>(words + base);
+		uint4 *dst = reinterpret_cast<uint4 *>(img);
+		for (uint32_t i = threadIdx.x; i < (bw + 3u) / 4u; i += kGroupThreads)
+			dst[i] = src[i];
+		if (indexed) {
+			uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+			for (uint32_t i = threadIdx.x; i < tsize / 4u; i += kGroupThreads)
+				t4[i] = make_uint4(0u, 0u, 0u, 0u);
+		}
+	}
 	__syncthreads();
 
 	// phase A: every candidate of the bucket against the staged image (read-only).  A linear scan per candidate made
@@ -1714,6 +1897,8 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 
 	// ---- top-down ----
 	uint32_t deepest = 0;
+	bool fused_leaves = false;
+	uint64_t leaves_evaluated = 0;
 	for (uint32_t l = 0; l + 1 < L; ++l) {
 		LevelAlloc &in = levels[l];
 		HD_CUDA_TRY(in.init_up(false));
@@ -1723,9 +1908,33 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 			return HD_ERR_OVERFLOW;
 		}
 		LevelAlloc &out = levels[l + 1];
-		HD_CUDA_TRY(out.init(uint32_t(cap), uint32_t(cap_e), l + 2 == L, st));
 		// reset per-level cursors (stats keep accumulating)
 		HD_CUDA_TRY(cudaMemsetAsync(&s->ctr->next_items, 0, 3 * sizeof(uint32_t), st));
+		static const bool fuse_off = getenv("HD_EDIT_LEAF") != nullptr; // "half" / "lane": the separate leaf kernels
+		if (l + 2 == L && !terrain && !long_lists && !fuse_off) {
+			// ---- last inner level + leaves fused (k_down_leaf): the leaf level holds the CHANGED leaves only ----
+			HD_CUDA_TRY(out.init_compact_leaves(uint32_t(cap), st));
+			k_down_leaf<<<grid_for(cap), kBlock, 0, st>>>(g, p->words, edits_dev, s->filled_dev, in.v, out.v, s->ctr);
+			HD_LAUNCH_CHECK();
+			rs = read_counters(p, host);
+			if (rs != HD_OK)
+				return rs;
+			if (host.error) {
+				set_error("edit scratch overflow at the leaf level");
+				return HD_ERR_OVERFLOW;
+			}
+			out.v.n = host.next_items;
+			leaves_evaluated = host.stats[1];
+			fused_leaves = true;
+			if (out.v.n) {
+				deepest = l + 1;
+				HD_CUDA_TRY(out.init_up(true, false));
+				k_fill_u8<<<grid_for(out.v.n), kBlock, 0, st>>>(out.v.state, out.v.n, 1);
+				HD_LAUNCH_CHECK();
+			}
+			break;
+		}
+		HD_CUDA_TRY(out.init(uint32_t(cap), uint32_t(cap_e), l + 2 == L, st));
 		if (terrain)
 			k_down<true><<<grid_for(uint64_t(in.v.n) * 8), kBlock, 0, st>>>(g, l, p->words, edits_dev, s->filled_dev, in.v, out.v,
 			                                                                s->ctr, &s->ctr->next_items, &s->ctr->next_entries);
@@ -1753,15 +1962,25 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 	}
 
 	// ---- leaves ----
-	if (deepest == L - 1) {
+	if (deepest == L - 1 && fused_leaves) { // the leaves were evaluated by k_down_leaf; only the changed ones are here
+		LevelAlloc &lv = levels[L - 1];
+		rs = run_upsert(p, L - 1, lv.v.n, 2, lv.v.cand, lv.v.state, lv.v.winner, lv.v.cur, lv.v.result);
+		if (rs != HD_OK)
+			return rs;
+		k_resolve<<<grid_for(lv.v.n), kBlock, 0, st>>>(lv.v, levels[L - 2].v.child_new, s->ctr);
+		HD_LAUNCH_CHECK();
+	} else if (deepest == L - 1) {
 		LevelAlloc &lv = levels[L - 1];
 		HD_CUDA_TRY(lv.init_up(true));
 		// one warp per 32 leaves; at least ~8 warps per SM-slot worth of grid so that small levels still spread out
 		const uint32_t leaf_grid = grid_for(uint64_t((lv.v.n + 31u) / 32u) * 32u);
+		static const bool use_half = getenv("HD_EDIT_LEAF") && !strcmp(getenv("HD_EDIT_LEAF"), "half");
 		if (terrain)
 			k_leaf<true><<<leaf_grid, kBlock, 0, st>>>(g, p->words, edits_dev, lv.v, s->ctr);
-		else
+		else if (use_half)
 			k_leaf_half<<<leaf_grid, kBlock, 0, st>>>(g, p->words, edits_dev, lv.v, s->ctr);
+		else
+			k_leaf_lane<<<grid_for(lv.v.n), kBlock, 0, st>>>(g, p->words, edits_dev, lv.v, s->ctr);
 		HD_LAUNCH_CHECK();
 		rs = run_upsert(p, L - 1, lv.v.n, 2, lv.v.cand, lv.v.state, lv.v.winner, lv.v.cur, lv.v.result);
 		if (rs != HD_OK)
@@ -1792,7 +2011,7 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 		stats->visited_nodes = 0;
 		for (uint32_t l = 0; l + 1 < L; ++l)
 			stats->visited_nodes += levels[l].v.n;
-		stats->visited_leaves = levels[L - 1].v.n;
+		stats->visited_leaves = fused_leaves ? leaves_evaluated : levels[L - 1].v.n;
 		stats->upserts = host.stats[2];
 		stats->appended_nodes = host.stats[3];
 		stats->appended_words = host.stats[4];
@@ -1841,7 +2060,7 @@ static hd_status fast_build(hd_pool *p) {
 	EditScratch *s = p->edit;
 	FastPath &f = s->fast;
 	const uint32_t L = g.node_levels;
-	static const uint32_t cap_max = getenv("HD_EDIT_FAST_CAP") ? uint32_t(atoi(getenv("HD_EDIT_FAST_CAP"))) : (1u << 18);
+	static const uint32_t cap_max = getenv("HD_EDIT_FAST_CAP") ? uint32_t(atoi(getenv("HD_EDIT_FAST_CAP"))) : (1u << 19);
 	f.lv.assign(L, LevelView{});
 	// pass 1 sizes the arena, pass 2 hands out the pointers
 	size_t total = 0;
