@@ -395,10 +395,37 @@ def run_ours(args):
             "colour_pool": {"paint_edits": COLOR_SPHERES + 1, "seconds": round(paint_s, 3),
                             "ms_per_paint_edit": round(paint_s / (COLOR_SPHERES + 1) * 1e3, 3)}}
 
-    parity, cpu_baseline = None, None
+    parity, cpu_baseline, cpu_ctx = None, None, None
     if rank == 0 and n == 1 and not args.no_cpu_baseline:
         parity = {}
-        cpu_baseline = cpu_trace_leg(pool, cfg, root, croot, args, parity)
+        cpu_baseline, cpu_ctx = cpu_trace_leg(pool, cfg, root, croot, args, parity)
+
+    # ---- coloured brush edits (vbr_edit of src/main.cpp:224-230, the reference's interactive right-mouse path) on the
+    # painted cfg2 scene: r = 128 spheres at visible surface points, 2 of 3 fill + colour, 1 of 3 paint only ----
+    if rank == 0 and n == 1:
+        g = pool.Trace(camera(cfg, root, 5, 96, 54, False, croot), want=("hits",))["hits"].reshape(-1)
+        g = g[(g["packed"] >> 31) != 0]
+        picks = g[np.linspace(0, len(g) - 1, 36).astype(int)] if len(g) else []
+        palette = [0xE04020, 0x20A040, 0x3060E0, 0xE0C020, 0xA040C0]
+        brushes = [(abi.sphere(tuple(int(c) for c in h["vox"]), 128 * 128), palette[i % 5], i % 3 == 2) for i, h in enumerate(picks)]
+        broot, ms = root, []
+        for d, rgb, paint in brushes:
+            t0 = time.perf_counter()
+            broot, _ = pool.EditColor(broot, d, rgb, paint)
+            ms.append((time.perf_counter() - t0) * 1e3)
+        if ms:
+            edit["color_brush"] = {"workload": "r=128 coloured sphere brushes at visible surface points of the painted cfg2 scene "
+                                               "(2 of 3 fill + colour, 1 of 3 paint), one hd_edit_color call each",
+                                   "edits": len(ms), "ms_per_edit_median": round(float(np.median(ms[4:])), 4),
+                                   "ms_per_edit_p90": round(float(np.percentile(ms[4:], 90)), 4)}
+            if cpu_ctx is not None and cpu_ctx["kind"] == "reference":
+                ref_ms = cpu_color_brush_leg(cpu_ctx, cfg, brushes[:12])
+                edit["color_brush"]["reference_ms_per_edit_median"] = ref_ms
+                edit["color_brush"]["speedup_vs_reference_cpu"] = round(ref_ms / edit["color_brush"]["ms_per_edit_median"], 2)
+                cpu_baseline["color_brush"] = {"ms_per_edit_median": ref_ms, "kind": "reference", "cores": os.cpu_count(),
+                                               "what": "ThreadedEdit(max_task_level = colour leaf level) through VBREditorWrapper, "
+                                                       "first 12 brushes of the same list on the reference-built scene (base coat only)"}
+    cpu_ctx = None
 
     # ---- BASELINE configs 3, 4, 5 on the 2^17 scene ----
     scene3 = cfg3_section(args, v, abi, replica, torch, dist, rank, n, local, dev, barrier, max_over_ranks, flush,
@@ -676,11 +703,29 @@ def cpu_trace_leg(pool, cfg, root, croot, args, parity):
             O.trace_frame_host(host.words_ptr, cfg.node_levels, P, row_step=ROW_STEP, threads=cores, want_pos=False)
         frames += 1
     dt = time.perf_counter() - t
-    return {"value": round(rays * frames / dt / 1e6, 3), "unit": "Mrays/s", "cores": cores, "kind": kind,
-            "sample": f"every {ROW_STEP}th row of the first {frames} benched 4K frames ({rays} rays/frame), full detail, "
-                      f"{'NodePoolTraversal::Traversal<float>' if kind == 'reference' else 'oracle port'} on {cores} threads "
-                      f"(geometry only: the host tracer has no colour path)",
-            "words_per_ray_F_sample": round(f_words / (3 * rays), 3)}
+    return ({"value": round(rays * frames / dt / 1e6, 3), "unit": "Mrays/s", "cores": cores, "kind": kind,
+             "sample": f"every {ROW_STEP}th row of the first {frames} benched 4K frames ({rays} rays/frame), full detail, "
+                       f"{'NodePoolTraversal::Traversal<float>' if kind == 'reference' else 'oracle port'} on {cores} threads "
+                       f"(geometry only: the host tracer has no colour path)",
+             "words_per_ray_F_sample": round(f_words / (3 * rays), 3)},
+            {"host": host, "hroot": hroot, "kind": kind})
+
+
+def cpu_color_brush_leg(ctx, cfg, brushes):
+    """The reference's coloured brush (VBREditorWrapper + VBRChunkWriter, VBREditor.hpp:26-107) on all host cores."""
+    from oracle import bindings as B
+    from vkhashdag_b200 import abi
+    cores = os.cpu_count() or 1
+    host, hroot = ctx["host"], ctx["hroot"]
+    cp = B.Ref().color_pool(COLOR_LEAF_LEVEL, node_capacity=1 << 22, leaf_word_capacity=1 << 28)
+    res = 1 << cfg.voxel_level
+    hroot = host.edit_color(cp, hroot, abi.sphere((res // 2,) * 3, 3 * res * res), 0x60C0E0, True, threads=cores)   # base coat
+    ms = []
+    for d, rgb, paint in brushes:
+        t0 = time.perf_counter()
+        hroot = host.edit_color(cp, hroot, d, rgb, paint, threads=cores)
+        ms.append((time.perf_counter() - t0) * 1e3)
+    return round(float(np.median(ms)), 4)
 
 
 def cfg3_parity_and_cpu_leg(pool3, cfg3, root_b, spheres, mirror_terrain, root3, edit, parity, cpu_baseline):

@@ -132,3 +132,27 @@ def test_color_random_brushes(oracle, ref, hd):
         else:
             steps.append((abi.sphere(c, r * r), int(rng.choice(palette)), False))
     run_sequence(oracle, ref, hd, cfg, 3, steps)[0].close()
+
+
+def test_color_large_leaves_many_macro_blocks(oracle, ref, hd):
+    """64^3-voxel colour leaves (16 macro blocks, 512 8^3 blocks each): the block path of color.cu — one-colour blocks from
+    the editor, from empty space and from single old runs next to per-voxel blocks, repeated rewrites in place and appends."""
+    cfg = abi.default_config(level_count=9, top_level_count=9)
+    steps = [(abi.terrain(cfg.voxel_level), None, False),
+             (abi.aabb((0, 0, 0), (512, 150, 512)), 0x40A040, False),
+             (abi.sphere((256, 160, 256), 90 ** 2), 0xC08040, False),
+             (abi.sphere((200, 150, 240), 70 ** 2), 0x2040F0, True),
+             (abi.sphere((200, 150, 240), 70 ** 2), 0x2040F0, True),       # same paint again: nothing changes
+             (abi.sphere((230, 170, 250), 33 ** 2), 0xF02020, True),
+             (abi.sphere((280, 190, 280), 40 ** 2, dig=True), None, False),
+             (abi.sphere((120, 140, 120), 50 ** 2), 0xF0F020, False),
+             (abi.aabb((100, 100, 100), (140, 190, 130)), 0x10D0D0, False),
+             (abi.sphere((128, 150, 128), 9 ** 2), 0x123456, True)]
+    dev, gr, rp, cp, rr, stats = run_sequence(oracle, ref, hd, cfg, 3, steps)
+    assert max(s[1] for s in stats) >= 8
+    rn, rl = cp.arrays()
+    Pg = abi.camera_params(cfg, gr, (0.5, 0.75, 1.2), np.pi, -0.45, 320, 180, color_root=dev.ColorRoot(), color_leaf_level=3)
+    Pr = abi.camera_params(cfg, rr, (0.5, 0.75, 1.2), np.pi, -0.45, 320, 180, color_root=cp.root, color_leaf_level=3)
+    got, exp = dev.Trace(Pg), oracle.trace_frame(rp.words_ptr, Pr, rn, rl)
+    assert np.array_equal(got["hits"], exp["hits"]) and np.array_equal(got["rgba8"], exp["rgba8"])
+    dev.close()

@@ -16,6 +16,7 @@
 #include "editors.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace hd {
@@ -23,6 +24,8 @@ namespace hd {
 constexpr int kCB = 256;
 constexpr uint32_t kTagNode = 0u, kTagColor = 1u, kTagLeaf = 2u, kTagNull = 3u; // src/DAGColorPool.hpp:26
 constexpr uint32_t kMacroBits = 14u;                                          // VBRColor.hpp:46-49
+constexpr uint32_t kBlkBits = 9u;      // the block path works on 8 x 8 x 8 voxel blocks (512 consecutive Morton indices)
+constexpr uint32_t kPerVoxel = 0xFFFFFFFFu; // block key: not one colour, evaluate voxel by voxel (no RGB8 colour has a high byte)
 constexpr uint32_t kCPending = 0xFFFFFFFEu; // not a valid pointer: tag 3 with data != 0 never occurs otherwise
 
 __device__ __forceinline__ uint32_t ctag(uint32_t p) { return p >> 30; }
@@ -97,6 +100,8 @@ __device__ inline void chunk_lookup(const uint32_t *__restrict__ lv, uint32_t id
 // ---- octree part (levels <= leaf_level): BFS work items ----------------------------------------------------------
 struct CItems {
 	uint32_t n, cap;
+	const uint32_t *n_dev; // device-resident item count (the one-sync octree pass) or NULL: then `n` is host-known
+	__device__ __forceinline__ uint32_t count() const { return n_dev ? min(*n_dev, cap) : n; }
 	uint32_t *geom;   // old geometry pointer of the node
 	uint32_t *oct;    // colour-octree pointer of the node before the edit
 	uint64_t *pos;    // x | y<<21 | z<<42
@@ -150,7 +155,7 @@ __global__ void __launch_bounds__(kCB) k_cdown(ColorEdit e, uint32_t level, cons
                                                const uint32_t *__restrict__ cnodes, CItems in, CItems inner, CItems leaf,
                                                uint32_t *counts) {
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, item = t >> 3, c = t & 7u;
-	if (item >= in.n)
+	if (item >= in.count())
 		return;
 	const uint32_t g = in.geom[item];
 	uint32_t child = kNull;
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__(kCB) k_cdown(ColorEdit e, uint32_t level, cons
 __global__ void __launch_bounds__(kCB) k_cup(CItems it, uint32_t *cnodes, uint32_t *ctr, uint64_t node_cap, uint32_t *parent_child,
                                              uint32_t *root_out) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= it.n)
+	if (i >= it.count())
 		return;
 	uint32_t ch[8];
 	bool all_null = true, all_same = true;
@@ -232,9 +237,18 @@ __global__ void __launch_bounds__(kCB) k_cup(CItems it, uint32_t *cnodes, uint32
 // (VBREditorWrapper::EditNode below the leaf level + EditVoxel, VBREditor.hpp:60-80; editors main.cpp:47-69,107-149).
 __global__ void __launch_bounds__(kCB) k_voxels(ColorEdit e, const uint32_t *__restrict__ words, const uint32_t *__restrict__ cleaves,
                                                 CItems leaf, uint32_t first_leaf, uint32_t n_leaves, uint32_t sbits,
-                                                uint32_t *colors, uint8_t *bw) {
+                                                uint32_t *colors, uint8_t *bw, const uint32_t *__restrict__ block_list,
+                                                uint32_t n_listed) {
 	const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-	const uint32_t li = uint32_t(t >> sbits), m = uint32_t(t & ((1ull << sbits) - 1ull));
+	uint32_t li, m;
+	if (block_list) { // block path: only the voxels of the listed (mixed) 8^3 blocks are evaluated, output index = t
+		const uint32_t slot = uint32_t(t >> kBlkBits);
+		if (slot >= n_listed)
+			return;
+		const uint32_t blk = block_list[slot], bbits = sbits - kBlkBits;
+		li = blk >> bbits, m = ((blk & ((1u << bbits) - 1u)) << kBlkBits) | (uint32_t(t) & ((1u << kBlkBits) - 1u));
+	} else
+		li = uint32_t(t >> sbits), m = uint32_t(t & ((1ull << sbits) - 1ull));
 	if (li >= n_leaves)
 		return;
 	const uint32_t item = first_leaf + li;
@@ -365,13 +379,14 @@ hd_status exclusive_scan(hd_pool *p, const uint32_t *in, uint32_t *out, uint64_t
 }
 
 // words each leaf of the batch may have to append (0 when it will be rewritten in place); summed into *total
-__global__ void k_leaf_size(CItems leaf, uint32_t first_leaf, uint32_t n_leaves, uint32_t sbits, const uint32_t *__restrict__ flag,
+__global__ void k_leaf_size(CItems leaf, uint32_t first_leaf, uint32_t n_leaves, uint32_t sbits, uint32_t ebits, const uint32_t *__restrict__ flag,
                             const uint32_t *__restrict__ fscan, const uint32_t *__restrict__ bits, const uint32_t *__restrict__ bscan,
                             const uint32_t *__restrict__ cleaves, unsigned long long *total) {
 	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
 	if (li >= n_leaves)
 		return;
-	const uint64_t S = 1ull << sbits, a = uint64_t(li) << sbits, last = a + S - 1;
+	// the scan arrays hold 2^ebits elements per leaf: one per voxel (ebits == sbits) or one per 8^3 block (block path)
+	const uint64_t S = 1ull << sbits, a = uint64_t(li) << ebits, last = a + (1ull << ebits) - 1;
 	const uint32_t block_cnt = fscan[last] + flag[last] - fscan[a], total_bits = bscan[last] + bits[last] - bscan[a];
 	const uint32_t data = uint32_t((S + (1u << kMacroBits) - 1u) >> kMacroBits) * 2u + block_cnt * 2u + ((total_bits + 31u) >> 5) + 4u;
 	uint32_t append = (data & 1u) ? data + 1u : data;
@@ -386,13 +401,13 @@ __global__ void k_leaf_size(CItems leaf, uint32_t first_leaf, uint32_t n_leaves,
 
 // per leaf: sizes, allocation (in place if it fits, else append with capacity doubling: DAGColorPool::SetLeaf,
 // DAGColorPool.hpp:173-204 with keep_history = false), header words; thread per leaf
-__global__ void k_leaf_alloc(CItems leaf, uint32_t first_leaf, uint32_t n_leaves, uint32_t sbits, const uint32_t *__restrict__ flag,
+__global__ void k_leaf_alloc(CItems leaf, uint32_t first_leaf, uint32_t n_leaves, uint32_t sbits, uint32_t ebits, const uint32_t *__restrict__ flag,
                              const uint32_t *__restrict__ fscan, const uint32_t *__restrict__ bits, const uint32_t *__restrict__ bscan,
                              uint32_t *cleaves, uint32_t *ctr, uint64_t leaf_cap, uint32_t *chunk_idx) {
 	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
 	if (li >= n_leaves)
 		return;
-	const uint64_t S = 1ull << sbits, a = uint64_t(li) << sbits, last = a + S - 1;
+	const uint64_t S = 1ull << sbits, a = uint64_t(li) << ebits, last = a + (1ull << ebits) - 1;
 	const uint32_t block_cnt = fscan[last] + flag[last] - fscan[a];
 	const uint32_t total_bits = bscan[last] + bits[last] - bscan[a];
 	const uint32_t macro_cnt = uint32_t((S + (1u << kMacroBits) - 1u) >> kMacroBits);
@@ -488,9 +503,230 @@ __global__ void __launch_bounds__(kCB) k_emit(uint64_t n, uint32_t sbits, const 
 	}
 }
 
+// ---- block path: re-encode at 8^3-block granularity ----------------------------------------------------------------------
+// The voxel path above touches every voxel of every touched colour leaf (2 M voxels per 128^3 leaf) although most of a leaf
+// ends up as long single-colour runs: everything the editor covers, every EMPTY region (an empty voxel takes the editor's
+// colour, main.cpp:64-69,143-149) and every untouched solid region that was one colour before.  Here a thread first classifies
+// each 8^3 block (512 consecutive Morton indices) by walking the old geometry and the editor's node rule down to the block:
+// either the whole block is ONE colour with no weights (its key), or it is listed for the per-voxel evaluation.  Block starts,
+// prefix sums, sizes and the emit then run over blocks; only listed blocks are expanded to voxels.  The chunk produced is the
+// same canonical encoding, word for word (tests/test_gpu_color_edit.py compares against the reference's writer).
+
+// is [m0, m0 + 512) covered by ONE run without weights of the old chunk?  (a block never straddles a macro block)
+__device__ inline bool chunk_uniform_run(const uint32_t *__restrict__ lv, uint32_t idx, uint32_t m0, uint32_t &colors) {
+	const uint32_t macro_cnt = lv[idx + 1], block_cnt_all = lv[idx + 2];
+	const uint32_t macro_off = idx + 4, block_base = macro_off + (macro_cnt << 1);
+	const uint32_t macro_id = m0 >> kMacroBits;
+	const uint32_t mx = lv[macro_off + (macro_id << 1)];
+	uint32_t block_off = block_base + (mx << 1);
+	uint32_t block_cnt = macro_id + 1 < macro_cnt ? lv[macro_off + ((macro_id + 1) << 1)] - mx : block_cnt_all - mx;
+	const uint32_t end_off = block_off + (block_cnt << 1);
+	const uint32_t vid = m0 & ((1u << kMacroBits) - 1u);
+	while (block_cnt) { // first run with voxel_index_offset > vid
+		const uint32_t step = block_cnt >> 1;
+		if ((lv[block_off + (step << 1) + 1] >> 18) <= vid)
+			block_cnt -= step + 1, block_off += (step + 1) << 1;
+		else
+			block_cnt = step;
+	}
+	// block_off = the run after the one that holds vid; that run must start at or behind the end of the block
+	if (block_off < end_off && (lv[block_off + 1] >> 18) < vid + (1u << kBlkBits))
+		return false;
+	const uint32_t by = lv[block_off - 1];
+	colors = lv[block_off - 2];
+	return ((by >> 16) & 3u) == 0u;
+}
+
+struct BlockArrays {
+	uint32_t *key;      // colour of a one-colour block, or kPerVoxel
+	uint32_t *first_c, *last_c; // colors word of the block's first / last voxel
+	uint8_t *first_b, *last_b;  // bits per weight of the first / last voxel
+	uint32_t *runs;     // run starts inside the block (after k_block_flags: including the start at the block's first voxel)
+	uint32_t *bits;     // weight bits of the block
+	uint32_t *slot;     // index of a per-voxel block in the compact list
+	uint8_t *start;     // a run starts at the block's first voxel
+};
+
+// thread per (leaf, 8^3 block): classification (the walk of k_voxels, stopped at the block's node)
+__global__ void __launch_bounds__(kCB) k_cblock(ColorEdit e, const uint32_t *__restrict__ words, const uint32_t *__restrict__ cleaves,
+                                                CItems leaf, uint32_t first_leaf, uint32_t n_leaves, uint32_t sbits, BlockArrays B,
+                                                uint32_t *list, uint32_t *list_count) {
+	const uint32_t bbits = sbits - kBlkBits;
+	const uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t li = blk >> bbits;
+	uint32_t key = kPerVoxel;
+	const bool valid = li < n_leaves;
+	if (valid) {
+		const uint32_t m0 = (blk & ((1u << bbits) - 1u)) << kBlkBits, item = first_leaf + li;
+		const uint32_t oct = leaf.oct[item];
+		const bool has_fill = ctag(oct) == kTagColor, has_src = ctag(oct) == kTagLeaf;
+		const uint32_t fill_rgb8 = cdata(oct), src = cdata(oct);
+		const uint64_t p = leaf.pos[item];
+		uint32_t x = uint32_t(p) & 0x1FFFFFu, y = uint32_t(p >> 21) & 0x1FFFFFu, z = uint32_t(p >> 42) & 0x1FFFFFu;
+		uint32_t g = leaf.geom[item];
+		const uint32_t block_level = e.voxel_level - 3u;
+		for (uint32_t L = e.leaf_level + 1u; L <= block_level; ++L) {
+			const uint32_t c = (m0 >> (3u * (e.voxel_level - L))) & 7u;
+			uint32_t child = kNull;
+			if (g != kNull) {
+				const uint32_t mask = words[g];
+				if (mask >> c & 1u)
+					child = words[g + 1u + __popc(mask & ((1u << c) - 1u))];
+			}
+			x = (x << 1) | (c & 1u), y = (y << 1) | ((c >> 1) & 1u), z = (z << 1) | ((c >> 2) & 1u);
+			bool color_set;
+			const EditType et = color_edit_node(e, e.voxel_level - L, x, y, z, child == kNull, has_fill, fill_rgb8, color_set);
+			if (color_set) { // writer->Push(color, subtree): the whole block
+				key = e.rgb8;
+				break;
+			}
+			if (et != kProceed) { // writer->Copy(subtree, fill): one colour only if the old chunk has one run there
+				if (!has_src)
+					key = has_fill ? fill_rgb8 : 0u;
+				else {
+					uint32_t c_old;
+					if (chunk_uniform_run(cleaves, src, m0, c_old))
+						key = c_old;
+				}
+				break;
+			}
+			g = child;
+		}
+		B.key[blk] = key;
+		if (key != kPerVoxel) {
+			B.first_c[blk] = B.last_c[blk] = key;
+			B.first_b[blk] = B.last_b[blk] = 0;
+			B.runs[blk] = 0u, B.bits[blk] = 0u;
+		}
+	}
+	// compact list of the per-voxel blocks (warp-aggregated)
+	const bool want = valid && key == kPerVoxel;
+	const uint32_t vote = __ballot_sync(0xFFFFFFFFu, want), lane = threadIdx.x & 31u;
+	if (vote) {
+		uint32_t base = 0;
+		if (lane == uint32_t(__ffs(vote) - 1))
+			base = atomicAdd(list_count, __popc(vote));
+		base = __shfl_sync(0xFFFFFFFFu, base, __ffs(vote) - 1);
+		if (want) {
+			const uint32_t sl = base + __popc(vote & ((1u << lane) - 1u));
+			list[sl] = blk, B.slot[blk] = sl;
+		}
+	}
+}
+
+// warp per listed block: first / last key, run starts inside the block, weight bits (from the per-voxel arrays)
+__global__ void __launch_bounds__(kCB) k_block_summary(uint32_t n_listed, const uint32_t *__restrict__ list, const uint32_t *__restrict__ colors,
+                                                       const uint8_t *__restrict__ bw, BlockArrays B) {
+	const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+	if (slot >= n_listed)
+		return;
+	const uint32_t base = slot << kBlkBits;
+	uint32_t starts = 0, bits = 0;
+	for (uint32_t v = lane; v < (1u << kBlkBits); v += 32u) { // coalesced: consecutive lanes, consecutive voxels
+		const uint32_t c = colors[base + v], b = bw[base + v] & 3u;
+		bits += b;
+		if (v)
+			starts += (c != colors[base + v - 1] || b != (bw[base + v - 1] & 3u)) ? 1u : 0u;
+	}
+	for (int d = 16; d; d >>= 1)
+		starts += __shfl_xor_sync(0xFFFFFFFFu, starts, d), bits += __shfl_xor_sync(0xFFFFFFFFu, bits, d);
+	if (lane == 0) {
+		const uint32_t blk = list[slot], last = base + (1u << kBlkBits) - 1u;
+		B.first_c[blk] = colors[base], B.first_b[blk] = bw[base] & 3u;
+		B.last_c[blk] = colors[last], B.last_b[blk] = bw[last] & 3u;
+		B.runs[blk] = starts, B.bits[blk] = bits;
+	}
+}
+
+// thread per block: does a run start at the block's first voxel?  (macro block starts, or the key differs from the previous voxel)
+__global__ void __launch_bounds__(kCB) k_block_flags(uint32_t n_blocks, uint32_t sbits, BlockArrays B) {
+	const uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;
+	if (blk >= n_blocks)
+		return;
+	const uint32_t b = blk & ((1u << (sbits - kBlkBits)) - 1u);
+	bool start = ((b << kBlkBits) & ((1u << kMacroBits) - 1u)) == 0u;
+	if (!start)
+		start = B.first_c[blk] != B.last_c[blk - 1] || B.first_b[blk] != B.last_b[blk - 1];
+	B.start[blk] = start ? 1 : 0;
+	B.runs[blk] += start ? 1u : 0u;
+}
+
+// thread per block: macro-block table entries, and the header of a one-colour block that starts a run
+__global__ void __launch_bounds__(kCB) k_emit_blocks(uint32_t n_blocks, uint32_t sbits, BlockArrays B, const uint32_t *__restrict__ rscan,
+                                                     const uint32_t *__restrict__ wscan, const uint32_t *__restrict__ chunk_idx,
+                                                     uint32_t *cleaves) {
+	const uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;
+	if (blk >= n_blocks)
+		return;
+	const uint32_t bbits = sbits - kBlkBits, li = blk >> bbits, idx = chunk_idx[li];
+	if (idx == 0xFFFFFFFFu)
+		return;
+	const uint32_t a = li << bbits, m0 = (blk - a) << kBlkBits;
+	const uint32_t macro_cnt = cleaves[idx + 1];
+	const uint32_t macro_off = idx + 4u, block_off = macro_off + macro_cnt * 2u;
+	const uint32_t run = rscan[blk] - rscan[a], bit = wscan[blk] - wscan[a];
+	if ((m0 & ((1u << kMacroBits) - 1u)) == 0u) {
+		cleaves[macro_off + ((m0 >> kMacroBits) << 1)] = run;     // first_block
+		cleaves[macro_off + ((m0 >> kMacroBits) << 1) + 1] = bit; // weight_start
+	}
+	if (B.key[blk] != kPerVoxel && B.start[blk]) {
+		const uint32_t macro_first = a + ((m0 >> kMacroBits) << (kMacroBits - kBlkBits));
+		cleaves[block_off + (run << 1)] = B.key[blk];
+		cleaves[block_off + (run << 1) + 1] = ((m0 & ((1u << kMacroBits) - 1u)) << 18) | (bit - (wscan[macro_first] - wscan[a]));
+	}
+}
+
+// CTA of 512 threads per listed block: headers and weight bits of its voxels (k_emit restricted to one block, with the
+// run / bit indices inside the block from a CTA-wide scan)
+__global__ void __launch_bounds__(1u << kBlkBits) k_emit_listed(uint32_t sbits, const uint32_t *__restrict__ list, const uint32_t *__restrict__ colors,
+                                                                const uint8_t *__restrict__ bw, BlockArrays B, const uint32_t *__restrict__ rscan,
+                                                                const uint32_t *__restrict__ wscan, const uint32_t *__restrict__ chunk_idx,
+                                                                uint32_t *cleaves) {
+	__shared__ uint32_t s_runs[17], s_bits[17];
+	const uint32_t slot = blockIdx.x, v = threadIdx.x, lane = v & 31u, warp = v >> 5;
+	const uint32_t blk = list[slot], bbits = sbits - kBlkBits, li = blk >> bbits, idx = chunk_idx[li];
+	const uint32_t t = (slot << kBlkBits) + v;
+	const uint32_t c = colors[t], b = bw[t] & 3u, w = uint32_t(bw[t]) >> 2;
+	const bool flag = v ? (c != colors[t - 1] || b != (bw[t - 1] & 3u)) : B.start[blk] != 0;
+	// exclusive scans of (flag, b) over the 512 threads
+	uint32_t fr = flag ? 1u : 0u, fb = b;
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, fr, d), q = __shfl_up_sync(0xFFFFFFFFu, fb, d);
+		if (lane >= uint32_t(d))
+			fr += o, fb += q;
+	}
+	if (lane == 31u)
+		s_runs[warp + 1] = fr, s_bits[warp + 1] = fb;
+	__syncthreads();
+	if (v == 0) {
+		s_runs[0] = s_bits[0] = 0u;
+		for (int k = 1; k <= 16; ++k)
+			s_runs[k] += s_runs[k - 1], s_bits[k] += s_bits[k - 1];
+	}
+	__syncthreads();
+	if (idx == 0xFFFFFFFFu)
+		return;
+	const uint32_t a = li << bbits, m = ((blk - a) << kBlkBits) | v;
+	const uint32_t run = rscan[blk] - rscan[a] + s_runs[warp] + fr - (flag ? 1u : 0u);
+	const uint32_t bit = wscan[blk] - wscan[a] + s_bits[warp] + fb - b;
+	const uint32_t macro_cnt = cleaves[idx + 1], block_cnt = cleaves[idx + 2];
+	const uint32_t macro_off = idx + 4u, block_off = macro_off + macro_cnt * 2u, weight_off = block_off + block_cnt * 2u;
+	if (flag) {
+		const uint32_t macro_first = a + ((m >> kMacroBits) << (kMacroBits - kBlkBits));
+		cleaves[block_off + (run << 1)] = c;
+		cleaves[block_off + (run << 1) + 1] = ((m & ((1u << kMacroBits) - 1u)) << 18) | (b << 16) | (bit - (wscan[macro_first] - wscan[a]));
+	}
+	if (b) {
+		const uint32_t o = bit & 31u;
+		atomicOr(&cleaves[weight_off + (bit >> 5)], w << o);
+		if (o + b > 32u)
+			atomicOr(&cleaves[weight_off + (bit >> 5) + 1], w >> (32u - o));
+	}
+}
+
 __global__ void k_leaf_report(CItems leaf, uint32_t *parent_child, uint32_t *root_out) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= leaf.n)
+	if (i >= leaf.count())
 		return;
 	const uint32_t par = leaf.parent[i];
 	if (par == 0xFFFFFFFFu)
@@ -517,12 +753,30 @@ struct CLevel {
 			return e;
 		return cudaSuccess;
 	}
+	bool owned = true;
+	// the same arrays carved out of one arena (the one-sync octree pass allocates every level up front)
+	static size_t arena_bytes(uint32_t cap, bool inner) {
+		return ((size_t(cap) * (4 + 4 + 8 + 4 + 4 + (inner ? 32 : 0))) + 255) & ~size_t(255);
+	}
+	void init_from(char *&ptr, uint32_t cap, bool inner, cudaStream_t stream) {
+		s = stream, v = CItems{}, v.cap = cap, owned = false;
+		char *q = ptr;
+		v.pos = reinterpret_cast<uint64_t *>(q), q += size_t(cap) * 8;
+		v.geom = reinterpret_cast<uint32_t *>(q), q += size_t(cap) * 4;
+		v.oct = reinterpret_cast<uint32_t *>(q), q += size_t(cap) * 4;
+		v.parent = reinterpret_cast<uint32_t *>(q), q += size_t(cap) * 4;
+		v.result = reinterpret_cast<uint32_t *>(q), q += size_t(cap) * 4;
+		if (inner)
+			v.child = reinterpret_cast<uint32_t *>(q);
+		ptr += arena_bytes(cap, inner);
+	}
 	void release() {
 		void *ptrs[] = {v.geom, v.oct, v.pos, v.parent, v.result, v.child};
-		for (void *q : ptrs)
-			if (q)
-				cudaFreeAsync(q, s);
-		v = CItems{};
+		if (owned)
+			for (void *q : ptrs)
+				if (q)
+					cudaFreeAsync(q, s);
+		v = CItems{}, owned = true;
 	}
 };
 
@@ -669,14 +923,75 @@ hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, 
 		HD_CUDA_TRY(cudaStreamSynchronize(s));
 		return HD_OK;
 	};
+	const uint32_t col_root_in = p->color_root;
+	HD_CUDA_TRY(cudaMemcpyAsync(root_dev, &col_root_in, 4, cudaMemcpyHostToDevice, s));
+	uint32_t deepest = 0;
+	// ---- octree levels, optimistic: ONE host round trip.  A brush touches a handful of octree nodes per level, so every
+	// level gets a fixed-capacity queue up front, the kernels read their item counts from device memory, and all the counts
+	// come back together.  A queue that turns out too small (a huge edit) is detected there; nothing has been written to the
+	// colour pool yet, so the pass is simply redone level by level with exact sizes (the code below it).
+	char *arena = nullptr;
+	uint32_t *lvl_counts = nullptr;
+	ScopeExit free_arena{[&]() {
+		if (arena)
+			cudaFreeAsync(arena, s);
+		if (lvl_counts)
+			cudaFreeAsync(lvl_counts, s);
+	}};
+	bool sized = false;
+	static const bool one_sync = !(getenv("HD_COLOR_ONE_SYNC") && atoi(getenv("HD_COLOR_ONE_SYNC")) == 0);
+	if (one_sync) {
+		constexpr uint32_t kInnerCap = 2048, kLeafCap = 8192;
+		auto cap_of = [&](uint32_t l) { return l >= 4 ? kInnerCap : std::min<uint32_t>(kInnerCap, 1u << (3 * l)); };
+		size_t bytes = CLevel::arena_bytes(kLeafCap, false);
+		for (uint32_t l = 0; l <= LL; ++l)
+			bytes += CLevel::arena_bytes(cap_of(l), true);
+		HD_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&arena), bytes, s));
+		HD_CUDA_TRY(cmalloc(&lvl_counts, 4 * (LL + 2), s));
+		HD_CUDA_TRY(cudaMemsetAsync(lvl_counts, 0, size_t(4) * (LL + 2) * 4, s));
+		char *q = arena;
+		for (uint32_t l = 0; l <= LL; ++l) {
+			inner[l].init_from(q, cap_of(l), true, s);
+			inner[l].v.n_dev = lvl_counts + 4 * l; // block l: what produced level l ([0] inner items, [1] leaves, [3] overflow)
+		}
+		leaf.init_from(q, kLeafCap, false, s);
+		leaf.v.n_dev = lvl_counts + 4 * LL + 1;
+		k_croot<<<1, 32, 0, s>>>(e, root_in, col_root_in, inner[0].v, leaf.v, lvl_counts, root_dev);
+		HD_LAUNCH_CHECK();
+		for (uint32_t l = 0; l < LL; ++l) {
+			k_cdown<<<cblocks(uint64_t(cap_of(l)) * 8), kCB, 0, s>>>(e, l, p->words, p->color_nodes, inner[l].v, inner[l + 1].v, leaf.v,
+			                                                       lvl_counts + 4 * (l + 1));
+			HD_LAUNCH_CHECK();
+		}
+		std::vector<uint32_t> hcs(4 * (LL + 2));
+		HD_CUDA_TRY(cudaMemcpyAsync(hcs.data(), lvl_counts, hcs.size() * 4, cudaMemcpyDeviceToHost, s));
+		HD_CUDA_TRY(cudaStreamSynchronize(s));
+		sized = true;
+		for (uint32_t l = 0; l <= LL && sized; ++l)
+			sized = hcs[4 * l + 3] == 0 && hcs[4 * l] <= cap_of(l);
+		const uint32_t n_leaves = LL == 0 ? hcs[1] : hcs[4 * LL + 1];
+		sized = sized && n_leaves <= kLeafCap;
+		if (sized) {
+			for (uint32_t l = 0; l <= LL; ++l) {
+				inner[l].v.n = hcs[4 * l], inner[l].v.n_dev = nullptr;
+				if (inner[l].v.n)
+					deepest = l;
+			}
+			leaf.v.n = n_leaves, leaf.v.n_dev = nullptr;
+		} else {
+			for (auto &l : inner)
+				l.release();
+			leaf.release();
+		}
+	}
+	if (!sized) {
+	// ---- octree levels, exact: one round trip per level ----
 	// leaf items can be created from any octree level's expansion: size the leaf list for the worst case lazily
 	// (grown by re-running is avoided: capacity = 8 x the widest inner level, which bounds the leaves of one level;
 	// leaves only appear at level LL, i.e. from the expansion of level LL-1, or the root when LL == 0)
 	HD_CUDA_TRY(inner[0].init(1, true, s));
 	HD_CUDA_TRY(leaf.init(1, false, s));
 	HD_CUDA_TRY(cudaMemsetAsync(counts, 0, 16, s));
-	const uint32_t col_root_in = p->color_root;
-	HD_CUDA_TRY(cudaMemcpyAsync(root_dev, &col_root_in, 4, cudaMemcpyHostToDevice, s));
 	k_croot<<<1, 32, 0, s>>>(e, root_in, col_root_in, inner[0].v, leaf.v, counts, root_dev);
 	HD_LAUNCH_CHECK();
 	st = read_counts();
@@ -685,7 +1000,7 @@ hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, 
 		return st;
 	}
 	inner[0].v.n = hc[0], leaf.v.n = hc[1];
-	uint32_t deepest = 0;
+	deepest = 0;
 	for (uint32_t l = 0; l < LL && inner[l].v.n; ++l) {
 		const uint64_t cap = uint64_t(inner[l].v.n) * 8;
 		if (cap > 0x7FFFFFF0ull) {
@@ -710,11 +1025,99 @@ hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, 
 			leaf.v.n = hc[1];
 		deepest = l + 1;
 	}
+	}
 
-	// ---- leaves: per-voxel colours -> canonical VBR chunks, in batches of <= 2^26 voxels ----
 	const uint32_t n_leaf = leaf.v.n;
 	uint64_t leaf_voxels = 0;
-	if (n_leaf) {
+	static const bool block_path = !(getenv("HD_COLOR_BLOCKS") && atoi(getenv("HD_COLOR_BLOCKS")) == 0);
+	if (n_leaf && block_path && sbits > kBlkBits) {
+		// ---- block path: classify 8^3 blocks, expand only the mixed ones to voxels (see k_cblock) ----
+		const uint32_t bbits = sbits - kBlkBits;
+		const uint32_t per_batch = std::max<uint32_t>(1u, (1u << 24) >> bbits);
+		for (uint32_t first = 0; first < n_leaf; first += per_batch) {
+			const uint32_t nl = std::min(per_batch, n_leaf - first), nb = nl << bbits;
+			BlockArrays B{};
+			uint32_t *list = nullptr, *list_count = nullptr, *rscan = nullptr, *wscan = nullptr, *chunk_idx = nullptr, *colors = nullptr;
+			uint8_t *bw = nullptr;
+			unsigned long long *total = nullptr;
+			ScopeExit free_batch{[&]() {
+				void *ptrs[] = {B.key, B.first_c, B.last_c, B.first_b, B.last_b, B.runs, B.bits, B.slot, B.start, list, list_count,
+				                rscan, wscan, chunk_idx, colors, bw, total};
+				for (void *q : ptrs)
+					if (q)
+						cudaFreeAsync(q, s);
+			}};
+			HD_CUDA_TRY(cmalloc(&B.key, nb, s));
+			HD_CUDA_TRY(cmalloc(&B.first_c, nb, s));
+			HD_CUDA_TRY(cmalloc(&B.last_c, nb, s));
+			HD_CUDA_TRY(cmalloc(&B.first_b, nb, s));
+			HD_CUDA_TRY(cmalloc(&B.last_b, nb, s));
+			HD_CUDA_TRY(cmalloc(&B.runs, nb, s));
+			HD_CUDA_TRY(cmalloc(&B.bits, nb, s));
+			HD_CUDA_TRY(cmalloc(&B.slot, nb, s));
+			HD_CUDA_TRY(cmalloc(&B.start, nb, s));
+			HD_CUDA_TRY(cmalloc(&list, nb, s));
+			HD_CUDA_TRY(cmalloc(&list_count, 1, s));
+			HD_CUDA_TRY(cmalloc(&rscan, nb, s));
+			HD_CUDA_TRY(cmalloc(&wscan, nb, s));
+			HD_CUDA_TRY(cmalloc(&chunk_idx, nl, s));
+			HD_CUDA_TRY(cmalloc(&total, 1, s));
+			HD_CUDA_TRY(cudaMemsetAsync(list_count, 0, 4, s));
+			HD_CUDA_TRY(cudaMemsetAsync(total, 0, 8, s));
+			k_cblock<<<cblocks(nb), kCB, 0, s>>>(e, p->words, p->color_leaves, leaf.v, first, nl, sbits, B, list, list_count);
+			HD_LAUNCH_CHECK();
+			uint32_t n_listed = 0;
+			HD_CUDA_TRY(cudaMemcpyAsync(&n_listed, list_count, 4, cudaMemcpyDeviceToHost, s));
+			HD_CUDA_TRY(cudaStreamSynchronize(s));
+			const uint64_t nv = uint64_t(n_listed) << kBlkBits;
+			leaf_voxels += nv;
+			if (n_listed) {
+				HD_CUDA_TRY(cmalloc(&colors, nv, s));
+				HD_CUDA_TRY(cmalloc(&bw, nv, s));
+				k_voxels<<<cblocks(nv), kCB, 0, s>>>(e, p->words, p->color_leaves, leaf.v, first, nl, sbits, colors, bw, list, n_listed);
+				HD_LAUNCH_CHECK();
+				k_block_summary<<<cblocks(uint64_t(n_listed) * 32u), kCB, 0, s>>>(n_listed, list, colors, bw, B);
+				HD_LAUNCH_CHECK();
+			}
+			k_block_flags<<<cblocks(nb), kCB, 0, s>>>(nb, sbits, B);
+			HD_LAUNCH_CHECK();
+			st = exclusive_scan(p, B.runs, rscan, nb);
+			if (st == HD_OK)
+				st = exclusive_scan(p, B.bits, wscan, nb);
+			if (st != HD_OK)
+				return st;
+			unsigned long long need = 0;
+			k_leaf_size<<<cblocks(nl), kCB, 0, s>>>(leaf.v, first, nl, sbits, bbits, B.runs, rscan, B.bits, wscan, p->color_leaves, total);
+			HD_LAUNCH_CHECK();
+			HD_CUDA_TRY(cudaMemcpyAsync(&need, total, 8, cudaMemcpyDeviceToHost, s));
+			HD_CUDA_TRY(cudaStreamSynchronize(s));
+			st = ensure_color_storage(p, p->color_node_words, p->color_leaf_words + need);
+			if (st != HD_OK)
+				return st;
+			k_leaf_alloc<<<cblocks(nl), kCB, 0, s>>>(leaf.v, first, nl, sbits, bbits, B.runs, rscan, B.bits, wscan, p->color_leaves, p->color_ctr,
+			                                        p->color_leaf_cap, chunk_idx);
+			HD_LAUNCH_CHECK();
+			k_color_mark_dirty<<<cblocks(nl), kCB, 0, s>>>(chunk_idx, nl, uint32_t(std::min<uint64_t>(p->color_synced_leaf_words, 0xFFFFFFFFull)),
+			                                              p->color_dirty_list, p->color_dirty_ctr, kColorDirtyCap);
+			HD_LAUNCH_CHECK();
+			k_zero_weights<<<std::min<uint32_t>(nl, 1184u), kCB, 0, s>>>(nl, chunk_idx, p->color_leaves);
+			HD_LAUNCH_CHECK();
+			k_emit_blocks<<<cblocks(nb), kCB, 0, s>>>(nb, sbits, B, rscan, wscan, chunk_idx, p->color_leaves);
+			HD_LAUNCH_CHECK();
+			if (n_listed) {
+				k_emit_listed<<<n_listed, 1u << kBlkBits, 0, s>>>(sbits, list, colors, bw, B, rscan, wscan, chunk_idx, p->color_leaves);
+				HD_LAUNCH_CHECK();
+			}
+			if (first + per_batch < n_leaf) { // another batch follows: its storage check needs the words used so far
+				uint32_t ctr[4];
+				HD_CUDA_TRY(cudaMemcpyAsync(ctr, p->color_ctr, sizeof(ctr), cudaMemcpyDeviceToHost, s));
+				HD_CUDA_TRY(cudaStreamSynchronize(s));
+				p->color_leaf_words = ctr[1];
+			}
+		}
+		k_leaf_report<<<cblocks(n_leaf), kCB, 0, s>>>(leaf.v, LL ? inner[LL - 1].v.child : nullptr, root_dev);
+		HD_LAUNCH_CHECK();
+	} else if (n_leaf) {
 		const uint32_t per_batch = std::max<uint32_t>(1u, uint32_t((1ull << 26) >> sbits));
 		for (uint32_t first = 0; first < n_leaf; first += per_batch) {
 			const uint32_t nl = std::min(per_batch, n_leaf - first);
@@ -729,7 +1132,7 @@ hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, 
 			HD_CUDA_TRY(cmalloc(&fscan, n, s));
 			HD_CUDA_TRY(cmalloc(&bscan, n, s));
 			HD_CUDA_TRY(cmalloc(&chunk_idx, nl, s));
-			k_voxels<<<cblocks(n), kCB, 0, s>>>(e, p->words, p->color_leaves, leaf.v, first, nl, sbits, colors, bw);
+			k_voxels<<<cblocks(n), kCB, 0, s>>>(e, p->words, p->color_leaves, leaf.v, first, nl, sbits, colors, bw, nullptr, 0u);
 			HD_LAUNCH_CHECK();
 			k_flags<<<cblocks(n), kCB, 0, s>>>(colors, bw, n, sbits, flag, bits);
 			HD_LAUNCH_CHECK();
@@ -740,7 +1143,7 @@ hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, 
 				unsigned long long *total = nullptr, need = 0;
 				HD_CUDA_TRY(cmalloc(&total, 1, s));
 				HD_CUDA_TRY(cudaMemsetAsync(total, 0, 8, s));
-				k_leaf_size<<<cblocks(nl), kCB, 0, s>>>(leaf.v, first, nl, sbits, flag, fscan, bits, bscan, p->color_leaves, total);
+				k_leaf_size<<<cblocks(nl), kCB, 0, s>>>(leaf.v, first, nl, sbits, sbits, flag, fscan, bits, bscan, p->color_leaves, total);
 				HD_LAUNCH_CHECK();
 				HD_CUDA_TRY(cudaMemcpyAsync(&need, total, 8, cudaMemcpyDeviceToHost, s));
 				HD_CUDA_TRY(cudaStreamSynchronize(s));
@@ -748,7 +1151,7 @@ hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, 
 				st = ensure_color_storage(p, p->color_node_words, p->color_leaf_words + need);
 			}
 			if (st == HD_OK) {
-				k_leaf_alloc<<<cblocks(nl), kCB, 0, s>>>(leaf.v, first, nl, sbits, flag, fscan, bits, bscan, p->color_leaves, p->color_ctr,
+				k_leaf_alloc<<<cblocks(nl), kCB, 0, s>>>(leaf.v, first, nl, sbits, sbits, flag, fscan, bits, bscan, p->color_leaves, p->color_ctr,
 				                                        p->color_leaf_cap, chunk_idx);
 				HD_LAUNCH_CHECK();
 				k_color_mark_dirty<<<cblocks(nl), kCB, 0, s>>>(chunk_idx, nl, uint32_t(std::min<uint64_t>(p->color_synced_leaf_words, 0xFFFFFFFFull)),
