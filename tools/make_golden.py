@@ -34,7 +34,10 @@ def desc_dict(d):
     return {"kind": d.kind, "p0": list(d.p0), "p1": list(d.p1), "aux": d.aux, "r2": int(d.r2)}
 
 
-def main():
+def main(out_dir=None):
+    global OUT
+    if out_dir:
+        OUT = out_dir
     B.build(ref=True)
     R, O = B.Ref(), B.Oracle()
     os.makedirs(OUT, exist_ok=True)
@@ -189,4 +192,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)
