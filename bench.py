@@ -325,8 +325,13 @@ def run_ours(args):
     # memory.  hd_trace_submit/collect keeps two frames in flight (the reference keeps kFrameCount = 3,
     # src/main.cpp:20), so the read-back of frame k overlaps the trace of frame k+1; every frame is collected and
     # folded into a checksum inside the timed region.  `e2e_sync` is the same loop with the blocking hd_trace call.
-    hosts = [torch.zeros(local_px, dtype=torch.int32).pin_memory() for _ in range(2)]
-    views = [h.numpy().view(np.uint32) for h in hosts]
+    # The frame buffers are page-locked (hd_host_alloc).  With N GPUs writing frames into one socket's memory the host's DMA
+    # write rate is what bounds e2e: `d2h_copy_only_GBps_slowest_rank` below times the same copies with no kernel at all
+    # (measured on this pool's 8-GPU box: 54.6 GB/s alone, 11.85 GB/s per GPU with eight ranks copying = ~95 GB/s aggregate,
+    # which the pipelined frames reach).  HD_BENCH_WC=1 allocates write-combined buffers instead (43 GB/s alone: slower here).
+    use_wc = os.environ.get("HD_BENCH_WC", "0") != "0"
+    hosts = [v.HostBuffer(local_px, write_combined=use_wc) for _ in range(2)]
+    views = [h.array for h in hosts]
 
     def e2e_loop(steps, first):
         acc = 0
@@ -334,14 +339,27 @@ def run_ours(args):
             slot = s & 1
             if s >= 2:
                 pool.TraceCollect(slot)
-                acc ^= int(views[slot][::4099].sum())
+                acc ^= int(views[slot][::65537].sum())
             pool.TraceSubmit(camera(cfg, root, first + s, GW, GH, False, croot), views[slot], slot, shard=shard)
         for s in range(max(steps - 2, 0), steps):
             pool.TraceCollect(s & 1)
-            acc ^= int(views[s & 1][::4099].sum())
+            acc ^= int(views[s & 1][::65537].sum())
         return acc
 
     e2e_loop(3, 500)
+    # ceiling of the read-back alone: every rank copies a frame-sized device buffer to its host buffer back to back
+    copy_stream = torch.cuda.Stream(device=local)
+    host_t = torch.from_numpy(views[0].view(np.int32))   # a tensor view of the page-locked buffer: copy_ is a plain async D2H
+    barrier()
+    tc = time.perf_counter()
+    with torch.cuda.stream(copy_stream):
+        for _ in range(args.steps):
+            host_t.copy_(rgba, non_blocking=True)
+        copy_stream.synchronize()
+    my_copy_s = time.perf_counter() - tc
+    barrier()
+    copy_rate = -max_over_ranks(-(local_px * 4 * args.steps / my_copy_s / 1e9))[0]
+    del host_t
     barrier()
     te = time.perf_counter()
     checksum = e2e_loop(args.steps, 0) & 0xFFFFFFFF
@@ -400,31 +418,6 @@ def run_ours(args):
         parity = {}
         cpu_baseline, cpu_ctx = cpu_trace_leg(pool, cfg, root, croot, args, parity)
 
-    # ---- coloured brush edits (vbr_edit of src/main.cpp:224-230, the reference's interactive right-mouse path) on the
-    # painted cfg2 scene: r = 128 spheres at visible surface points, 2 of 3 fill + colour, 1 of 3 paint only ----
-    if rank == 0 and n == 1:
-        g = pool.Trace(camera(cfg, root, 5, 96, 54, False, croot), want=("hits",))["hits"].reshape(-1)
-        g = g[(g["packed"] >> 31) != 0]
-        picks = g[np.linspace(0, len(g) - 1, 36).astype(int)] if len(g) else []
-        palette = [0xE04020, 0x20A040, 0x3060E0, 0xE0C020, 0xA040C0]
-        brushes = [(abi.sphere(tuple(int(c) for c in h["vox"]), 128 * 128), palette[i % 5], i % 3 == 2) for i, h in enumerate(picks)]
-        broot, ms = root, []
-        for d, rgb, paint in brushes:
-            t0 = time.perf_counter()
-            broot, _ = pool.EditColor(broot, d, rgb, paint)
-            ms.append((time.perf_counter() - t0) * 1e3)
-        if ms:
-            edit["color_brush"] = {"workload": "r=128 coloured sphere brushes at visible surface points of the painted cfg2 scene "
-                                               "(2 of 3 fill + colour, 1 of 3 paint), one hd_edit_color call each",
-                                   "edits": len(ms), "ms_per_edit_median": round(float(np.median(ms[4:])), 4),
-                                   "ms_per_edit_p90": round(float(np.percentile(ms[4:], 90)), 4)}
-            if cpu_ctx is not None and cpu_ctx["kind"] == "reference":
-                ref_ms = cpu_color_brush_leg(cpu_ctx, cfg, brushes[:12])
-                edit["color_brush"]["reference_ms_per_edit_median"] = ref_ms
-                edit["color_brush"]["speedup_vs_reference_cpu"] = round(ref_ms / edit["color_brush"]["ms_per_edit_median"], 2)
-                cpu_baseline["color_brush"] = {"ms_per_edit_median": ref_ms, "kind": "reference", "cores": os.cpu_count(),
-                                               "what": "ThreadedEdit(max_task_level = colour leaf level) through VBREditorWrapper, "
-                                                       "first 12 brushes of the same list on the reference-built scene (base coat only)"}
     cpu_ctx = None
 
     # ---- BASELINE configs 3, 4, 5 on the 2^17 scene ----
@@ -449,6 +442,7 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": 84,
                     "d2h_bytes_per_step": int(local_px * 4 * n), "frame_checksum": checksum,
                     "value_blocking_call": round(e2e_sync_value, 2), "d2h_GBps_slowest_rank": round(d2h_rate, 2),
+                    "d2h_copy_only_GBps_slowest_rank": round(copy_rate, 2), "host_buffers": "write-combined pinned" if use_wc else "pinned",
                     "how": "hd_trace_submit/collect per step (2 frames in flight), wall clock incl. the D2H of every shaded "
                            "frame into pinned host memory (allocated after pinning the process to the GPU's NUMA node); "
                            "value_blocking_call = same loop through the blocking hd_trace"},
@@ -517,8 +511,28 @@ def cfg3_section(args, v, abi, replica, torch, dist, rank, n, local, dev, barrie
                          "appended_words": st["appended_words"], "scan_words": st["scan_words"], "path": st["path"],
                          "pool_used_MB": round(pool3.UsedWords() * 4 / 1e6, 1)}
         pool3.SetRoot(root_b)
+        # ---- coloured brush edits (vbr_edit of src/main.cpp:224-230, the reference's interactive right-mouse path) in the
+        # reference's own configuration: 2^17 world, colour leaf level 10 (128^3-voxel colour leaves, main.cpp:195-211) ----
+        pool3.ColorConfig(COLOR_LEAF_LEVEL)
+        res3 = 1 << vl3
+        _, _ = pool3.EditColor(root_b, abi.sphere((res3 // 2,) * 3, 3 * res3 * res3), 0x60C0E0, paint=True)   # base coat
+        g = pool3.Trace(camera(cfg3, root_b, 5, 96, 54, False, scale=scale), want=("hits",))["hits"].reshape(-1)
+        g = g[(g["packed"] >> 31) != 0]
+        picks = g[np.linspace(0, len(g) - 1, 36).astype(int)] if len(g) else []
+        palette = [0xE04020, 0x20A040, 0x3060E0, 0xE0C020, 0xA040C0]
+        brushes = [(abi.sphere(tuple(int(c) for c in h["vox"]), 128 * 128), palette[i % 5], i % 3 == 2) for i, h in enumerate(picks)]
+        broot, ms = root_b, []
+        for d, rgb, paint in brushes:
+            t0 = time.perf_counter()
+            broot, _ = pool3.EditColor(broot, d, rgb, paint)
+            ms.append((time.perf_counter() - t0) * 1e3)
+        if ms:
+            edit["color_brush"] = {"workload": "r=128 coloured sphere brushes at visible surface points of the edited cfg3 scene, colour leaf "
+                                               "level 10 (2 of 3 fill + colour, 1 of 3 paint), one hd_edit_color call each",
+                                   "edits": len(ms), "ms_per_edit_median": round(float(np.median(ms[4:])), 4),
+                                   "ms_per_edit_p90": round(float(np.percentile(ms[4:], 90)), 4)}
         if parity is not None:
-            cfg3_parity_and_cpu_leg(pool3, cfg3, root_b, spheres, mirror3, root3, edit, parity, cpu_baseline)
+            cfg3_parity_and_cpu_leg(pool3, cfg3, root_b, spheres, mirror3, root3, edit, parity, cpu_baseline, brushes[:12])
             mirror3 = None
     # ---- replicas: ONE packed broadcast of everything rank 0 built (the same path every later edit takes) ----
     sync = None
@@ -728,7 +742,7 @@ def cpu_color_brush_leg(ctx, cfg, brushes):
     return round(float(np.median(ms)), 4)
 
 
-def cfg3_parity_and_cpu_leg(pool3, cfg3, root_b, spheres, mirror_terrain, root3, edit, parity, cpu_baseline):
+def cfg3_parity_and_cpu_leg(pool3, cfg3, root_b, spheres, mirror_terrain, root3, edit, parity, cpu_baseline, brushes=()):
     """N = 1: the reference applies the SAME cfg3 sequence (terrain patch, then the 10 000 spheres one ThreadedEdit call
     each, NodePool.hpp:405-417 / NodePoolThreadedEdit.hpp:104-126) — its wall time is the CPU baseline of the edit
     metric and its canonical DAG must equal the GPU batch's.  Also the edit roofline of SURVEY §8d."""
@@ -753,8 +767,8 @@ def cfg3_parity_and_cpu_leg(pool3, cfg3, root_b, spheres, mirror_terrain, root3,
     alg_bytes = 4.0 * (k_read + k_write + S) * b["upserts"] + 16.0 * b["visited_leaves"]
     peak, peak_src = measured_peak()
     ach = alg_bytes / b["seconds"] / 1e9
-    edit["roofline"] = {"bound": "hbm", "kernel": "hd_edit_batch (all kernels of the batch; dominant: k_leaf_half, k_down, "
-                                                  "k_upsert_grouped — launch list in profiles/)",
+    edit["roofline"] = {"bound": "hbm", "kernel": "hd_edit_batch (all kernels of the batch; dominant: k_upsert_grouped, k_down_leaf, "
+                                                  "k_dedup — launch list in profiles/r2_launch_list_edit_cfg3.csv)",
                         "achieved": round(ach, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / peak, 5),
                         "traffic": ncu_static("edit_batch_dram_bytes"),
                         "traffic_source": "profiles/trace_ncu_summary.json (static ncu capture of the batch), or null",
@@ -793,6 +807,13 @@ def cfg3_parity_and_cpu_leg(pool3, cfg3, root_b, spheres, mirror_terrain, root3,
                             "what": "the WHOLE cfg3 batch: ThreadedEdit(busy_pool(cores), max_task_level=10), one call per edit, "
                                     "10 000 edits in index order"}
     edit["batch"]["speedup_vs_reference_cpu"] = round(batch_s / b["seconds"], 1)
+    if brushes and "color_brush" in edit:   # the same coloured brushes through the reference's VBREditorWrapper on its own scene
+        ref_ms = cpu_color_brush_leg({"host": host, "hroot": hroot}, cfg3, brushes)
+        edit["color_brush"]["reference_ms_per_edit_median"] = ref_ms
+        edit["color_brush"]["speedup_vs_reference_cpu"] = round(ref_ms / edit["color_brush"]["ms_per_edit_median"], 2)
+        cpu_baseline["color_brush"] = {"ms_per_edit_median": ref_ms, "kind": "reference", "cores": cores,
+                                       "what": f"ThreadedEdit(max_task_level = colour leaf level) through VBREditorWrapper, first {len(brushes)} "
+                                               f"brushes of the same list on the reference-built cfg3 scene (base coat, then the brushes)"}
     host.close(), mirror.close()
 
 

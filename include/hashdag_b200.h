@@ -288,6 +288,14 @@ hd_status hd_gc(hd_pool *pool, const uint32_t *roots, uint32_t n_roots, uint32_t
 hd_status hd_pool_save(hd_pool *pool, const char *path);
 hd_status hd_pool_load(const char *path, int device, hd_pool **out);
 
+/* ---- pinned host buffers for frame read-back ----
+ * hd_trace_submit copies straight into the caller's buffer; it should be page-locked.  write_combined = 1 allocates it
+ * write-combined (cudaHostAllocWriteCombined): the DMA engine does not snoop the CPU caches, which raises the read-back
+ * rate when several GPUs write into the same socket's memory at once, at the price of slow CPU READS of the buffer (fine
+ * for a frame that goes on to a display / encoder, wrong for one the CPU post-processes). */
+hd_status hd_host_alloc(uint64_t bytes, int write_combined, void **out);
+hd_status hd_host_free(void *ptr);
+
 /* ---- introspection used by tests / benches ---- */
 hd_status hd_pool_used_words(hd_pool *pool, uint64_t *out); /* sum of bucket_words */
 hd_status hd_sync(hd_pool *pool);

@@ -5,4 +5,4 @@ the reference's pool interface used by tests and benches; it holds no compute an
 """
 from .abi import (COLOR_NULL, NULL, HdConfig, HdDefaultConfig, HdEditDesc, HdTraceParams, HIT_DTYPE, aabb,  # noqa: F401
                   camera_params, default_config, edit_array, random_spheres, sphere, terrain)
-from .api import (AABBEditor, DAGNodePool, HashDagError, SphereEditor, TerrainEditor, kernel_launches, lib)  # noqa: F401
+from .api import (AABBEditor, DAGNodePool, HashDagError, HostBuffer, SphereEditor, TerrainEditor, kernel_launches, lib)  # noqa: F401

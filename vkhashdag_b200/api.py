@@ -68,7 +68,7 @@ SYMBOLS = [
     "hd_pool_load", "hd_gc", "hd_trace_submit", "hd_trace_collect", "hd_beam_dev",
     "hd_trace_with_beam_dev", "hd_trace_with_beam", "hd_color_config", "hd_color_root", "hd_color_leaf_level",
     "hd_color_sizes", "hd_color_read", "hd_edit_color", "hd_edit_last_path",
-    "hd_tile_shard_locate", "hd_pool_read_subtree",
+    "hd_tile_shard_locate", "hd_pool_read_subtree", "hd_host_alloc", "hd_host_free",
 ]
 
 
@@ -147,6 +147,8 @@ def lib():
     L.hd_pool_load.argtypes = [C.c_char_p, ci, C.POINTER(vp)]
     L.hd_pool_used_words.argtypes = [vp, C.POINTER(u64)]
     L.hd_sync.argtypes = [vp]
+    L.hd_host_alloc.argtypes = [u64, ci, C.POINTER(vp)]
+    L.hd_host_free.argtypes = [vp]
     L.hd_kernel_launches.restype = u64
     _lib = L
     return L
@@ -155,6 +157,22 @@ def lib():
 def _check(status):
     if status != HD_OK:
         raise HashDagError(status, lib().hd_last_error().decode(errors="replace"))
+
+
+class HostBuffer:
+    """Page-locked host memory from hd_host_alloc as a numpy uint32 array (`.array`); write_combined=True for frame
+    read-back targets the CPU will not read much."""
+
+    def __init__(self, n_words, write_combined=False):
+        self._p = C.c_void_p()
+        _check(lib().hd_host_alloc(int(n_words) * 4, int(write_combined), C.byref(self._p)))
+        self.array = np.ctypeslib.as_array((C.c_uint32 * int(n_words)).from_address(self._p.value))
+
+    def free(self):
+        if self._p:
+            self.array = None
+            lib().hd_host_free(self._p)
+            self._p = C.c_void_p()
 
 
 def kernel_launches():

@@ -232,6 +232,19 @@ void hd_pool_destroy(hd_pool *p) {
 	delete p;
 }
 
+hd_status hd_host_alloc(uint64_t bytes, int write_combined, void **out) {
+	if (!out || bytes == 0)
+		return HD_ERR_INVALID;
+	*out = nullptr;
+	HD_CUDA_TRY(cudaHostAlloc(out, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+	return HD_OK;
+}
+hd_status hd_host_free(void *ptr) {
+	if (ptr)
+		HD_CUDA_TRY(cudaFreeHost(ptr));
+	return HD_OK;
+}
+
 hd_status hd_pool_get_config(const hd_pool *p, hd_config *out) {
 	if (!p || !out)
 		return HD_ERR_INVALID;
