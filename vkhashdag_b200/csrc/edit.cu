@@ -44,6 +44,7 @@ struct DevCounters {
 	uint32_t next_items;
 	uint32_t next_entries;
 	uint32_t has_long; // some list of the level just expanded is longer than 32 entries -> k_down_long must run
+	uint32_t has_huge; // ... longer than kHugeList entries -> k_down_huge (a CTA per list) must run
 	uint32_t root_out;
 	uint32_t error; // 1 = scratch overflow
 	// low-latency path (one CUDA graph, no host round trips): item / list-entry counts of every level stay on the device
@@ -285,21 +286,29 @@ __device__ inline WarpFiltered warp_filter_count(const hd_edit_desc *__restrict_
                                                  uint32_t cur, uint32_t filled_ptr) {
 	const uint32_t lane = threadIdx.x & 31u, full = 0xFFFFFFFFu;
 	WarpFiltered f{cur, 0u, 0u};
-	for (uint32_t done = 0; done < len; done += 32u) { // 32 entries at a time, from the back of the list
-		const uint32_t k = done + lane;
-		uint32_t t = kNotAffected;
-		if (k < len)
-			t = edit_node(edits[list[len - 1u - k]], bits, x, y, z);
-		const uint32_t term = __ballot_sync(full, t == kFill || t == kClear);
-		const uint32_t proc = __ballot_sync(full, t == kProceed);
-		if (term) {
-			const uint32_t first = __ffs(term) - 1u; // the terminal edit nearest to the end of the list
-			f.count += __popc(proc & ((1u << first) - 1u));
-			f.cur = __shfl_sync(full, t, first) == kFill ? filled_ptr : kNull;
-			f.start = len - (done + first);
-			return f;
+	// 128 entries at a time, from the back of the list: the four classifications of a lane are independent, so their
+	// list -> descriptor load chains are in flight together (one chunk of 32 per trip made the root pass of a 10 000-edit
+	// batch a chain of 626 serialised global round trips: 0.53 ms on one warp)
+	for (uint32_t done = 0; done < len; done += 128u) {
+		uint32_t t[4];
+#pragma unroll
+		for (uint32_t q = 0; q < 4u; ++q) {
+			const uint32_t k = done + q * 32u + lane;
+			t[q] = k < len ? uint32_t(edit_node(edits[list[len - 1u - k]], bits, x, y, z)) : uint32_t(kNotAffected);
 		}
-		f.count += __popc(proc);
+#pragma unroll
+		for (uint32_t q = 0; q < 4u; ++q) {
+			const uint32_t term = __ballot_sync(full, t[q] == kFill || t[q] == kClear);
+			const uint32_t proc = __ballot_sync(full, t[q] == kProceed);
+			if (term) {
+				const uint32_t first = __ffs(term) - 1u; // the terminal edit nearest to the end of the list
+				f.count += __popc(proc & ((1u << first) - 1u));
+				f.cur = __shfl_sync(full, t[q], first) == kFill ? filled_ptr : kNull;
+				f.start = len - (done + q * 32u + first);
+				return f;
+			}
+			f.count += __popc(proc);
+		}
 	}
 	return f;
 }
@@ -309,13 +318,22 @@ __device__ inline uint2 warp_filter_write(const hd_edit_desc *__restrict__ edits
                                           const WarpFiltered &f, uint32_t filled_ptr, uint32_t *dst) {
 	const uint32_t lane = threadIdx.x & 31u, full = 0xFFFFFFFFu;
 	uint32_t out = 0;
-	for (uint32_t base = f.start; base < len; base += 32u) {
-		const uint32_t idx = base + lane;
-		const bool keep = idx < len && edit_node(edits[list[idx]], bits, x, y, z) == kProceed;
-		const uint32_t proc = __ballot_sync(full, keep);
-		if (keep)
-			dst[out + __popc(proc & ((1u << lane) - 1u))] = list[idx];
-		out += __popc(proc);
+	for (uint32_t base = f.start; base < len; base += 128u) {
+		bool keep[4];
+		uint32_t e[4];
+#pragma unroll
+		for (uint32_t q = 0; q < 4u; ++q) {
+			const uint32_t idx = base + q * 32u + lane;
+			e[q] = idx < len ? list[idx] : 0u;
+			keep[q] = idx < len && edit_node(edits[e[q]], bits, x, y, z) == kProceed;
+		}
+#pragma unroll
+		for (uint32_t q = 0; q < 4u; ++q) {
+			const uint32_t proc = __ballot_sync(full, keep[q]);
+			if (keep[q])
+				dst[out + __popc(proc & ((1u << lane) - 1u))] = e[q];
+			out += __popc(proc);
+		}
 	}
 	__syncwarp();
 	uint32_t skip = 0;
@@ -360,6 +378,174 @@ __global__ void k_root(Geometry g, const hd_edit_desc *__restrict__ edits, uint3
 	phase_root(g, edits, n_edits, iota, filled, root, out, ctr);
 }
 
+// ---- CTA-cooperative filtering for huge lists (the first levels of a 10 000-edit batch) --------------------------------
+// One warp walking a 10 000-entry list costs 0.5 ms per (item, child) and there are only 1 + 8 + 64 of them: a whole CTA
+// takes a list instead.  Three passes over the list (the classification is recomputed rather than stored): the last
+// kFill / kClear, the number of kProceed edits behind it, and their ordered compaction (one CTA-wide scan per chunk).
+constexpr uint32_t kHugeList = 1024u;
+constexpr int kHugeThreads = 256;
+struct CtaFiltered {
+	uint32_t cur, count, start;
+};
+__device__ inline CtaFiltered cta_filter_count(const hd_edit_desc *__restrict__ edits, const uint32_t *__restrict__ list, uint32_t len,
+                                               uint32_t bits, uint32_t x, uint32_t y, uint32_t z, uint32_t cur, uint32_t filled_ptr,
+                                               uint32_t *s_tmp /* 2 words */) {
+	if (threadIdx.x == 0)
+		s_tmp[0] = 0u, s_tmp[1] = 0u;
+	__syncthreads();
+	uint32_t best = 0u; // (index + 1) << 1 | is_fill of the last terminal edit this thread saw
+	for (uint32_t k = threadIdx.x; k < len; k += blockDim.x) {
+		const EditType t = edit_node(edits[list[k]], bits, x, y, z);
+		if (t == kFill || t == kClear)
+			best = ((k + 1u) << 1) | (t == kFill ? 1u : 0u);
+	}
+	if (best)
+		atomicMax(&s_tmp[0], best);
+	__syncthreads();
+	const uint32_t term = s_tmp[0];
+	CtaFiltered f{cur, 0u, term >> 1};
+	if (term)
+		f.cur = (term & 1u) ? filled_ptr : kNull;
+	uint32_t mine = 0u;
+	for (uint32_t k = f.start + threadIdx.x; k < len; k += blockDim.x)
+		mine += edit_node(edits[list[k]], bits, x, y, z) == kProceed ? 1u : 0u;
+	for (int d = 16; d; d >>= 1)
+		mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
+	if ((threadIdx.x & 31u) == 0u && mine)
+		atomicAdd(&s_tmp[1], mine);
+	__syncthreads();
+	f.count = s_tmp[1];
+	__syncthreads();
+	return f;
+}
+// ordered compaction of the kProceed edits of list[start..len) into dst, then the leading no-ops are dropped: {skip, remaining}
+__device__ inline uint2 cta_filter_write(const hd_edit_desc *__restrict__ edits, const uint32_t *__restrict__ list, uint32_t len,
+                                         uint32_t bits, uint32_t x, uint32_t y, uint32_t z, const CtaFiltered &f, uint32_t filled_ptr,
+                                         uint32_t *dst, uint32_t *s_scan /* kHugeThreads / 32 + 2 words */) {
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+	uint32_t base = 0u;
+	for (uint32_t c0 = f.start; c0 < len; c0 += blockDim.x) {
+		const uint32_t idx = c0 + threadIdx.x;
+		const uint32_t e = idx < len ? list[idx] : 0u;
+		const bool keep = idx < len && edit_node(edits[e], bits, x, y, z) == kProceed;
+		const uint32_t vote = __ballot_sync(0xFFFFFFFFu, keep);
+		if (lane == 0u)
+			s_scan[warp] = __popc(vote);
+		__syncthreads();
+		uint32_t off = 0u, total = 0u;
+		for (uint32_t w = 0; w < nw; ++w) {
+			const uint32_t c = s_scan[w];
+			off += w < warp ? c : 0u, total += c;
+		}
+		if (keep)
+			dst[base + off + __popc(vote & ((1u << lane) - 1u))] = e;
+		base += total;
+		__syncthreads();
+	}
+	__threadfence_block();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t skip = 0u;
+		if (f.cur == kNull || f.cur == filled_ptr)
+			while (skip < base && is_noop(edits[dst[skip]].kind, f.cur, filled_ptr))
+				++skip;
+		s_scan[nw] = skip;
+	}
+	__syncthreads();
+	const uint32_t skip = s_scan[nw];
+	__syncthreads();
+	return make_uint2(skip, base - skip);
+}
+
+// Root classification for batches of more than kHugeList edits: one CTA instead of one warp (phase_root otherwise).
+__global__ void __launch_bounds__(kHugeThreads) k_root_cta(Geometry g, const hd_edit_desc *__restrict__ edits, uint32_t n_edits,
+                                                           const uint32_t *__restrict__ iota, const uint32_t *__restrict__ filled,
+                                                           uint32_t root, LevelView out, DevCounters *ctr) {
+	__shared__ uint32_t s_tmp[2], s_scan[kHugeThreads / 32 + 2];
+	const uint32_t bits = g.voxel_level();
+	const CtaFiltered f = cta_filter_count(edits, iota, n_edits, bits, 0, 0, 0, root, filled[0], s_tmp);
+	uint2 r = make_uint2(0u, 0u);
+	if (f.count)
+		r = cta_filter_write(edits, iota, n_edits, bits, 0, 0, 0, f, filled[0], out.lists, s_scan);
+	if (threadIdx.x != 0)
+		return;
+	if (r.y == 0) {
+		ctr->root_out = f.cur;
+		return;
+	}
+	ctr->next_items = 1;
+	ctr->next_entries = r.x + r.y;
+	ctr->lvl_items[0] = 1;
+	ctr->lvl_entries[0] = r.x + r.y;
+	out.cur[0] = f.cur;
+	out.pos[0] = 0;
+	out.parent[0] = 0xFFFFFFFFu;
+	out.list_off[0] = r.x;
+	out.list_len[0] = r.y;
+}
+
+// Top-down expansion of the items whose edit list is longer than kHugeList: one CTA per (item, child).
+__global__ void __launch_bounds__(kHugeThreads) k_down_huge(Geometry g, uint32_t level, const uint32_t *__restrict__ words,
+                                                            const hd_edit_desc *__restrict__ edits,
+                                                            const uint32_t *__restrict__ filled, LevelView in, LevelView out,
+                                                            DevCounters *ctr) {
+	__shared__ uint32_t s_tmp[2], s_scan[kHugeThreads / 32 + 2], s_off;
+	const uint32_t item = blockIdx.x >> 3, c = blockIdx.x & 7u;
+	if (item >= in.n)
+		return;
+	const uint32_t len = in.list_len[item];
+	if (len <= kHugeList)
+		return; // k_down / k_down_long
+	const uint32_t cur = in.cur[item];
+	uint32_t child = kNull;
+	if (cur != kNull) {
+		const uint32_t mask = words[cur];
+		if (mask >> c & 1u)
+			child = words[cur + 1u + __popc(mask & ((1u << c) - 1u))];
+	}
+	uint32_t x, y, z;
+	unpack_pos(in.pos[item], x, y, z);
+	x = (x << 1) | (c & 1u), y = (y << 1) | ((c >> 1) & 1u), z = (z << 1) | ((c >> 2) & 1u);
+	const uint32_t bits = g.voxel_level() - (level + 1u);
+	const uint32_t *list = in.lists + in.list_off[item];
+	const uint32_t fp = filled[level + 1u];
+	const CtaFiltered f = cta_filter_count(edits, list, len, bits, x, y, z, child, fp, s_tmp);
+	uint32_t result = f.cur;
+	if (f.count) {
+		if (threadIdx.x == 0)
+			s_off = atomicAdd(&ctr->next_entries, f.count);
+		__syncthreads();
+		const uint32_t entry_off = s_off;
+		if (entry_off + f.count > out.cap_entries) {
+			if (threadIdx.x == 0)
+				ctr->error = 1;
+			return;
+		}
+		const uint2 r = cta_filter_write(edits, list, len, bits, x, y, z, f, fp, out.lists + entry_off, s_scan);
+		if (r.y) {
+			if (threadIdx.x == 0) {
+				const uint32_t slot = atomicAdd(&ctr->next_items, 1u);
+				if (slot >= out.cap)
+					ctr->error = 1;
+				else {
+					out.cur[slot] = f.cur;
+					out.pos[slot] = pack_pos(x, y, z);
+					out.parent[slot] = (item << 3) | c;
+					out.list_off[slot] = entry_off + r.x;
+					out.list_len[slot] = r.y;
+					if (r.y > 32u)
+						ctr->has_long = 1;
+					if (r.y > kHugeList)
+						ctr->has_huge = 1;
+				}
+			}
+			result = kPending;
+		}
+	}
+	if (threadIdx.x == 0)
+		in.child_new[size_t(item) * 8u + c] = result;
+}
+
 // Top-down expansion of the (rare) items whose edit list is longer than 32: one warp per (item, child).
 __global__ void __launch_bounds__(kBlock) k_down_long(Geometry g, uint32_t level, const uint32_t *__restrict__ words,
                                                       const hd_edit_desc *__restrict__ edits,
@@ -370,8 +556,8 @@ __global__ void __launch_bounds__(kBlock) k_down_long(Geometry g, uint32_t level
 	if (item >= in.n) // host-sized launch only (lists longer than 32 never take the low-latency path)
 		return;
 	const uint32_t len = in.list_len[item];
-	if (len <= 32u)
-		return; // done by k_down
+	if (len <= 32u || (len > kHugeList && !in.n_dev))
+		return; // done by k_down / k_down_huge (host-driven path)
 	const uint32_t cur = in.cur[item];
 	uint32_t child = kNull;
 	if (cur != kNull) {
@@ -752,6 +938,7 @@ __global__ void __launch_bounds__(kBlock) k_down_leaf(Geometry g, const uint32_t
 	if (alloc_item(ctr, &ctr->next_items, &ctr->next_entries, changed, 0u, out.cap, out.cap_entries, slot, entry_off, s_alloc)) {
 		out.cur[slot] = base_ptr; // the bucket-full fallback of upsert_leaf (NodePool.hpp:195)
 		out.parent[slot] = (item << 3) | c;
+		out.state[slot] = 1; // every leaf of the compact level is a candidate
 		*reinterpret_cast<uint2 *>(out.cand + size_t(slot) * 2u) = make_uint2(n0, n1);
 		in.child_new[size_t(item) * 8u + c] = kPending;
 	}
@@ -1362,16 +1549,17 @@ struct LevelAlloc {
 		s = stream;
 		v.cap = cap, v.cap_entries = 0, v.n = 0;
 		cudaError_t e;
-		if ((e = amalloc(&v.cur, cap, s)) || (e = amalloc(&v.parent, cap, s)) || (e = amalloc(&v.cand, uint64_t(cap) * 2, s)))
+		if ((e = amalloc(&v.cur, cap, s)) || (e = amalloc(&v.parent, cap, s)) || (e = amalloc(&v.cand, uint64_t(cap) * 2, s)) ||
+		    (e = amalloc(&v.state, cap, s)))
 			return e;
 		return cudaSuccess;
 	}
 	// arrays only needed once the item count is known
-	cudaError_t init_up(bool leaf, bool with_cand = true) {
+	cudaError_t init_up(bool leaf, bool compact = false) { // compact: cand and state already exist (init_compact_leaves)
 		cudaError_t e;
-		if ((e = amalloc(&v.result, v.n, s)) || (e = amalloc(&v.state, v.n, s)) || (e = amalloc(&v.winner, v.n, s)))
+		if ((e = amalloc(&v.result, v.n, s)) || (e = amalloc(&v.winner, v.n, s)))
 			return e;
-		if (with_cand && (e = amalloc(&v.cand, uint64_t(v.n) * (leaf ? 2 : 9), s)))
+		if (!compact && ((e = amalloc(&v.state, v.n, s)) || (e = amalloc(&v.cand, uint64_t(v.n) * (leaf ? 2 : 9), s))))
 			return e;
 		if (!leaf && (e = amalloc(&v.child_new, uint64_t(v.n) * 8, s)))
 			return e;
@@ -1880,13 +2068,17 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 		terrain = edits_host[i].kind == HD_EDIT_TERRAIN_FILL;
 	levels.resize(L);
 	HD_CUDA_TRY(levels[0].init(1, n_edits, L == 1, st));
-	k_root<<<1, 32, 0, st>>>(g, edits_dev, n_edits, iota, s->filled_dev, root_in, levels[0].v, s->ctr, nullptr);
+	if (n_edits > kHugeList)
+		k_root_cta<<<1, kHugeThreads, 0, st>>>(g, edits_dev, n_edits, iota, s->filled_dev, root_in, levels[0].v, s->ctr);
+	else
+		k_root<<<1, 32, 0, st>>>(g, edits_dev, n_edits, iota, s->filled_dev, root_in, levels[0].v, s->ctr, nullptr);
 	HD_LAUNCH_CHECK();
 	DevCounters host{};
 	hd_status rs = read_counters(p, host);
 	if (rs != HD_OK)
 		return rs;
 	bool long_lists = n_edits > 32; // does the level about to be expanded hold a list longer than 32?
+	bool huge_lists = n_edits > kHugeList; // ... longer than kHugeList?
 	if (host.next_items == 0) { // the root was not entered at all
 		*root_out = host.root_out;
 		if (stats)
@@ -1909,7 +2101,7 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 		}
 		LevelAlloc &out = levels[l + 1];
 		// reset per-level cursors (stats keep accumulating)
-		HD_CUDA_TRY(cudaMemsetAsync(&s->ctr->next_items, 0, 3 * sizeof(uint32_t), st));
+		HD_CUDA_TRY(cudaMemsetAsync(&s->ctr->next_items, 0, 4 * sizeof(uint32_t), st));
 		static const bool fuse_off = getenv("HD_EDIT_LEAF") != nullptr; // "half" / "lane": the separate leaf kernels
 		if (l + 2 == L && !terrain && !long_lists && !fuse_off) {
 			// ---- last inner level + leaves fused (k_down_leaf): the leaf level holds the CHANGED leaves only ----
@@ -1928,9 +2120,7 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 			fused_leaves = true;
 			if (out.v.n) {
 				deepest = l + 1;
-				HD_CUDA_TRY(out.init_up(true, false));
-				k_fill_u8<<<grid_for(out.v.n), kBlock, 0, st>>>(out.v.state, out.v.n, 1);
-				HD_LAUNCH_CHECK();
+				HD_CUDA_TRY(out.init_up(true, true));
 			}
 			break;
 		}
@@ -1947,6 +2137,10 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 			                                                                 in.v, out.v, s->ctr);
 			HD_LAUNCH_CHECK();
 		}
+		if (huge_lists && uint64_t(in.v.n) * 8 <= 0x7FFFFFFFull) {
+			k_down_huge<<<in.v.n * 8u, kHugeThreads, 0, st>>>(g, l, p->words, edits_dev, s->filled_dev, in.v, out.v, s->ctr);
+			HD_LAUNCH_CHECK();
+		}
 		rs = read_counters(p, host);
 		if (rs != HD_OK)
 			return rs;
@@ -1956,6 +2150,7 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 		}
 		out.v.n = host.next_items;
 		long_lists = host.has_long != 0;
+		huge_lists = host.has_huge != 0;
 		if (out.v.n == 0)
 			break;
 		deepest = l + 1;
