@@ -176,3 +176,44 @@ def test_torchrun_two_gpu_nccl_replica_sync():
            "--width", "1280", "--height", "720"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MULTI-GPU CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_read_subtree_matches_word_reads(oracle, hd):
+    """hd_pool_read_subtree: breadth-first records of a subtree == the same nodes read word by word (what a host-side
+    visitor such as NodePoolBase::Iterate needs, test/test.cpp:36-52); depth and capacity limits are honoured."""
+    cfg = abi.default_config(level_count=7, top_level_count=9)
+    dev = hd.DAGNodePool(cfg)
+    root = dev.EditBatch(NULL, [abi.sphere((60, 60, 60), 40 ** 2), abi.aabb((5, 5, 5), (30, 20, 90))])
+    recs, truncated = dev.ReadSubtree(root)
+    assert not truncated and recs[0][0] == root and recs[0][1] == 0
+    seen = {}
+    for ptr, level, words in recs:
+        leaf = level == cfg.node_levels - 1
+        n = 2 if leaf else 1 + bin(int(dev.ReadWords(ptr, 1)[0]) & 0xFF).count("1")
+        assert words == [int(w) for w in dev.ReadWords(ptr, n)]
+        seen.setdefault(level, set()).add(ptr)
+    m = mirror_of(oracle, dev, cfg)
+    canon = oracle.canonical(m.words_ptr, cfg.node_levels, root)
+    assert [len(seen[l]) for l in range(cfg.node_levels)] == canon["per_level"]     # every reachable node, nothing else
+    top, _ = dev.ReadSubtree(root, depth=2)
+    assert {lvl for _, lvl, _ in top} == {0, 1} and len(top) == 1 + len(recs[0][2]) - 1
+    few, truncated = dev.ReadSubtree(root, capacity=10)
+    assert truncated and len(few) == 10
+    assert dev.ReadSubtree(NULL)[0] == []
+    dev.close()
+
+
+def test_host_buffers_for_frame_readback(hd):
+    """hd_host_alloc: page-locked (optionally write-combined) frame buffers for hd_trace_submit / collect."""
+    cfg = abi.default_config(level_count=7, top_level_count=9)
+    dev = hd.DAGNodePool(cfg)
+    root = dev.Edit(NULL, hd.SphereEditor((64, 64, 64), 40 ** 2))
+    P = abi.camera_params(cfg, root, (0.5, 0.5, 1.6), np.pi, 0.0, 128, 72, color_root=(1 << 30) | 0x4080C0)
+    ref = dev.Trace(P, want=("rgba8",))["rgba8"].reshape(-1)
+    for wc in (False, True):
+        buf = hd.HostBuffer(128 * 72, write_combined=wc)
+        dev.TraceSubmit(P, buf.array, 0)
+        dev.TraceCollect(0)
+        assert np.array_equal(np.array(buf.array), ref)
+        buf.free()
+    dev.close()
