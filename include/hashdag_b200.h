@@ -300,6 +300,11 @@ hd_status hd_host_free(void *ptr);
 hd_status hd_pool_used_words(hd_pool *pool, uint64_t *out); /* sum of bucket_words */
 hd_status hd_sync(hd_pool *pool);
 uint64_t hd_kernel_launches(void); /* kernels this library has launched so far (bench gpu_launches) */
+/* Exhaustive check of the trace kernel's exact-arithmetic shortcuts against the IEEE operations they stand for
+ * (trace.frag:83-88, 276-277, 340-356 are written with plain `/` and `sqrt`): the unchecked reciprocal over every float in
+ * [2^-51, 2^51), the unchecked square root over every float in [2^-100, 2^100), x / D for every 0 <= x <= D, D in {255, 63, 31,
+ * 7, 3}, and fma(h, c, t) == h * c + t for sampled power-of-two h.  *mismatches = number of differing results (0 = exact). */
+hd_status hd_selftest_exact_arith(int device, uint64_t *mismatches);
 
 #ifdef __cplusplus
 }

@@ -166,3 +166,86 @@ def test_beam_prepass_and_beam_trace(oracle, hd):
         same = (plain["hits"]["packed"] == got["hits"]["packed"]) & (plain["hits"]["vox"] == got["hits"]["vox"]).all(-1)
         assert both.sum() > 1000 and same[both].mean() > 0.98      # LOD bias differs by the beam term on a few pixels
     dev.close()
+
+
+def test_exact_arithmetic_helpers(hd):
+    """The trace kernel's shortcuts (unchecked reciprocal / square root, x / D with a folded reciprocal, the centre planes
+    as one fma) return the bits of the IEEE operations the shader writes, for every input they can see."""
+    assert hd.api.selftest_exact_arith(0) == 0
+
+
+def test_lean_frames_equal_the_oracle_on_a_frame_size_change(oracle, hd):
+    """The lean instantiation (rgba8 only: per-column / per-row ray tables, no iteration plane) against the oracle, with
+    the frame size changing between calls (the ray tables are rebuilt) and on odd sizes."""
+    cfg = abi.default_config(level_count=10, top_level_count=9)
+    opool = oracle.pool(cfg)
+    root = opool.edit_batch(NULL, [abi.terrain(cfg.voxel_level)] + abi.random_spheres(40, cfg.voxel_level, seed=4, rmin=8, rmax=70))
+    dev = hd.DAGNodePool(cfg)
+    dev.UploadFrom(opool)
+    for (W, H), cam in (((640, 360), ((0.5, 0.8, 0.5), 0.6, -0.6)), ((333, 517), ((0.2, 0.7, 0.9), 2.3, -0.3)),
+                        ((1280, 720), ((0.5, 1.05, 0.5), 0.1, -1.3)), ((640, 360), ((0.9, 0.6, 0.1), 4.0, -0.2))):
+        for lod in (False, True):
+            P = abi.camera_params(cfg, root, *cam, W, H, color_root=(1 << 30) | 0x80C040, lod=lod)
+            exp = oracle.trace_frame(opool.words_ptr, P)
+            got = dev.Trace(P, want=("rgba8",))
+            assert np.array_equal(got["rgba8"], exp["rgba8"]), (W, H, cam, lod)
+    dev.close()
+
+
+def test_staged_top_levels_equal_the_pool_path(oracle, hd):
+    """The staged copy of the top node levels (built once a root is traced for the second time) must not change a single
+    output: frames, hit records, iteration counts and F before and after the table exists, across edits (new roots),
+    a clear + re-upload, shards, and a DAG too shallow to stage anything."""
+    cfg = abi.default_config(level_count=10, top_level_count=9)
+    opool = oracle.pool(cfg)
+    roots = [opool.edit_batch(NULL, [abi.terrain(cfg.voxel_level)] + abi.random_spheres(30, cfg.voxel_level, seed=2, rmin=8, rmax=80))]
+    roots.append(opool.edit_batch(roots[0], abi.random_spheres(10, cfg.voxel_level, seed=3, rmin=20, rmax=90)))
+    dev = hd.DAGNodePool(cfg)
+    dev.UploadFrom(opool)
+    W, H = 480, 270
+    cams = [((0.5, 0.8, 0.5), 0.6, -0.6, False), ((0.2, 0.7, 0.9), 2.3, -0.3, True), ((0.5, 1.05, 0.5), 0.1, -1.3, False)]
+    for rnd in range(2):
+        for root in roots:
+            for k in range(3):            # the 2nd and 3rd frame of a root read the table
+                for cam in cams:
+                    P = abi.camera_params(cfg, root, *cam[:3], W, H, color_root=(1 << 30) | 0x4080C0, lod=cam[3])
+                    exp = oracle.trace_frame(opool.words_ptr, P)
+                    got = dev.Trace(P, want=("rgba8", "hits", "iters", "fetches"))
+                    for key in ("rgba8", "hits", "iters", "fetches"):
+                        assert np.array_equal(got[key], exp[key]), (rnd, root, k, cam, key)
+                    lean = dev.Trace(P, want=("rgba8",))
+                    assert np.array_equal(lean["rgba8"], exp["rgba8"]), (rnd, root, k, cam, "lean")
+                    sh = dev.Trace(P, want=("rgba8",), shard=(64, 64, 1, 2))
+                    ref_sh = oracle_shard(exp["rgba8"], P, (64, 64, 1, 2), dev)
+                    assert np.array_equal(sh["rgba8"], ref_sh), (rnd, root, k, cam, "shard")
+        dev.Clear()                        # invalidates the table; the same pointers come back with the re-upload
+        dev.UploadFrom(opool)
+    dev.close()
+    # 2 node levels: nothing can be staged, the pool path serves every frame
+    cfg2 = abi.default_config(level_count=3, top_level_count=9)
+    op2 = oracle.pool(cfg2)
+    r2 = op2.edit_batch(NULL, [abi.sphere((4, 4, 4), 9)])
+    d2 = hd.DAGNodePool(cfg2)
+    d2.UploadFrom(op2)
+    for k in range(3):
+        P = abi.camera_params(cfg2, r2, (0.5, 0.5, 1.6), np.pi, 0.0, 160, 90, color_root=(1 << 30) | 0x112233)
+        exp = oracle.trace_frame(op2.words_ptr, P)
+        got = d2.Trace(P)
+        for key in ("rgba8", "hits", "iters"):
+            assert np.array_equal(got[key], exp[key]), (k, key)
+    d2.close()
+
+
+def oracle_shard(frame, P, shard, dev):
+    """Rearrange a full frame into the tile-major layout hd_trace_tiles returns for `shard` = (tile_w, tile_h, rank, world)."""
+    from vkhashdag_b200 import replica
+    tw, th, rank, world = shard
+    H, W = frame.shape
+    tiles = replica.local_tiles(W, H, tw, th, rank, world)
+    out = np.zeros(len(tiles) * tw * th, np.uint32)
+    for lt, tx, ty in tiles:
+        tile = np.zeros((th, tw), np.uint32)
+        part = frame[ty * th:(ty + 1) * th, tx * tw:(tx + 1) * tw]
+        tile[:part.shape[0], :part.shape[1]] = part
+        out[lt * tw * th:(lt + 1) * tw * th] = tile.reshape(-1)
+    return out

@@ -24,6 +24,8 @@ inline float fmin2(float a, float b) { return b < a ? b : a; }
 inline float fmax2(float a, float b) { return a < b ? b : a; }
 
 enum Want { kFetch, kTest, kPush, kPop, kDone };
+// per-scale census of the transitions (simt_hist): [scale][0 push, 1 advance, 2 pop (arrival scale)]
+uint64_t g_hist[kStack + 1][3];
 
 struct Lane {
 	const uint32_t *nodes;
@@ -95,6 +97,7 @@ struct Lane {
 		if (tc_max < h)
 			stack[scale] = parent;
 		h = tc_max;
+		g_hist[scale][0]++;
 		if (scale > leaf_scale)
 			parent = nodes[parent + 1u + uint32_t(__builtin_popcount(child_bits & (child_mask - 1u)))];
 		else
@@ -113,6 +116,7 @@ struct Lane {
 				step_mask ^= 1u << i, pos[i] -= scale_exp2;
 		t_min = tc_max;
 		idx ^= step_mask;
+		g_hist[scale][1]++;
 		return (idx & step_mask) != 0;
 	}
 	void pop() {
@@ -126,6 +130,7 @@ struct Lane {
 			return;
 		}
 		scale_exp2 = fbits((scale - kStack + 127u) << 23);
+		g_hist[scale][2]++;
 		parent = stack[scale];
 		uint32_t sh[3];
 		for (int i = 0; i < 3; ++i)
@@ -392,6 +397,12 @@ void run_warp_greedy(const uint32_t *nodes, const hd_trace_params &P, const std:
 } // namespace
 
 extern "C" {
+// per-scale transition census accumulated by every simt_model call so far; clear = 1 resets it afterwards
+void simt_hist(uint64_t *out /* [24][3] */, int clear) {
+	std::memcpy(out, g_hist, sizeof(g_hist));
+	if (clear)
+		std::memset(g_hist, 0, sizeof(g_hist));
+}
 // out[0..4] = warp instructions, thread instructions, rays, warp trips, hits; then per region {executions, lanes, cost}.
 // Samples every `cta_step`-th 16x8 CTA patch of the frame.  `per_warp_patches` > 1 gives each warp that many 8x4 patches
 // (stacked vertically) as its refill queue.

@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--frames", type=int, default=3)
     ap.add_argument("--cta-step", type=int, default=97)
     ap.add_argument("--breakdown", action="store_true")
+    ap.add_argument("--hist", action="store_true", help="only print the per-level census of PUSH / ADVANCE / POP transitions")
     a = ap.parse_args()
     so = os.path.join(ROOT, "tools", "_simt_model.so")
     subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tools", "simt_model.cpp")])
@@ -57,6 +58,21 @@ def main():
                              C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
     cfg, host, root = scene(a.level)
     bench.LEVEL_COUNT = a.level
+    if a.hist:
+        for f in range(a.frames):
+            P = bench.camera(cfg, root, f * 7, 3840, 2160, False)
+            out = (C.c_uint64 * 32)()
+            L.simt_model(host.words_ptr, C.byref(P), 0, 0, 1, a.cta_step, None, out)
+        h = (C.c_uint64 * (24 * 3))()
+        L.simt_hist(h, 1)
+        h = np.array(h[:], np.uint64).reshape(24, 3).astype(np.float64)
+        tot = h.sum()
+        print("level (0 = root's children)  push%  advance%  pop-to%   cumulative share of all transitions")
+        cum = 0.0
+        for scale in range(22, 22 - a.level - 1, -1):
+            cum += h[scale].sum()
+            print(f"  level {22 - scale:2d}   {100 * h[scale, 0] / tot:6.2f} {100 * h[scale, 1] / tot:6.2f} {100 * h[scale, 2] / tot:6.2f}    {100 * cum / tot:6.2f}")
+        return
     rows = []
     for name, policy, refill_min, patches in (("baseline (one transition per trip)", 0, 0, 1),
                                               ("two-phase (advance until PUSH/POP)", 1, 0, 1),

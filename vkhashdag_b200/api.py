@@ -68,7 +68,7 @@ SYMBOLS = [
     "hd_pool_load", "hd_gc", "hd_trace_submit", "hd_trace_collect", "hd_beam_dev",
     "hd_trace_with_beam_dev", "hd_trace_with_beam", "hd_color_config", "hd_color_root", "hd_color_leaf_level",
     "hd_color_sizes", "hd_color_read", "hd_edit_color", "hd_edit_last_path",
-    "hd_tile_shard_locate", "hd_pool_read_subtree", "hd_host_alloc", "hd_host_free",
+    "hd_tile_shard_locate", "hd_pool_read_subtree", "hd_host_alloc", "hd_host_free", "hd_selftest_exact_arith",
 ]
 
 
@@ -150,6 +150,7 @@ def lib():
     L.hd_host_alloc.argtypes = [u64, ci, C.POINTER(vp)]
     L.hd_host_free.argtypes = [vp]
     L.hd_kernel_launches.restype = u64
+    L.hd_selftest_exact_arith.argtypes = [ci, C.POINTER(u64)]
     _lib = L
     return L
 
@@ -173,6 +174,13 @@ class HostBuffer:
             self.array = None
             lib().hd_host_free(self._p)
             self._p = C.c_void_p()
+
+
+def selftest_exact_arith(device=0):
+    """Mismatches between the trace kernel's exact-arithmetic shortcuts and the IEEE operations they replace (0 = exact)."""
+    n = C.c_uint64(0)
+    _check(lib().hd_selftest_exact_arith(int(device), C.byref(n)))
+    return int(n.value)
 
 
 def kernel_launches():

@@ -8,7 +8,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libhashdag_b200.so")
 SOURCES = ["pool.cu", "trace.cu", "edit.cu", "sync.cu", "gc.cu", "color.cu"]
 # trace.cu: -fmad=false — bit-exact fp32 parity with the reference arithmetic evaluated without contraction
-EXTRA = {"trace.cu": ["-fmad=false"]}
+# (and -ffp-contract=off for its host side, which evaluates the per-column / per-row ray coordinates)
+EXTRA = {"trace.cu": ["-fmad=false", "-Xcompiler", "-ffp-contract=off"]}
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -118,6 +118,21 @@ struct hd_pool {
 	hd_hit_record *stage_hits = nullptr;
 	uint64_t stage_pixels = 0;
 	hd_trace_params *params_dev = nullptr;
+	// per-column / per-row NDC coordinates of the pixel centres for the current frame size (trace.cu: ray_tables)
+	float *ray_table = nullptr;
+	uint64_t ray_cap = 0;
+	uint32_t ray_w = 0, ray_h = 0;
+	// staged top levels of the DAG below `tt_root` (trace.cu: trace_table_*): node levels [0, tt_levels) unfolded into a
+	// dense array of {child reference, child's mask} pairs, read with one 64-bit load per descent.  Nodes are immutable
+	// and buckets append-only, so a table stays valid for its root until the word space is rewritten (tt_invalidate()).
+	uint2 *tt_entries = nullptr;    // [tt_cap_nodes * 8]
+	uint32_t *tt_masks = nullptr;   // [tt_cap_nodes] child mask of every staged node
+	uint32_t *tt_list[2] = {nullptr, nullptr}; // BFS frontier (pool pointers), ping-pong
+	uint32_t *tt_count = nullptr;   // device counter
+	uint32_t tt_cap_nodes = 0, tt_root = HD_NULL_NODE, tt_levels = 0, tt_nodes = 0;
+	bool tt_valid = false;
+	uint32_t tt_seen_root = HD_NULL_NODE, tt_seen_frames = 0; // auto mode: build once a root has been traced twice
+	void tt_invalidate() { tt_valid = false, tt_seen_root = HD_NULL_NODE, tt_seen_frames = 0; }
 
 	// pipelined frames (hd_trace_submit / hd_trace_collect): two slots, copy stream overlaps the next trace
 	cudaStream_t copy_stream = nullptr;

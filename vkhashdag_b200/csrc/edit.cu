@@ -50,7 +50,19 @@ struct DevCounters {
 	// low-latency path (one CUDA graph, no host round trips): item / list-entry counts of every level stay on the device
 	uint32_t lvl_items[HD_MAX_NODE_LEVELS];
 	uint32_t lvl_entries[HD_MAX_NODE_LEVELS];
+	// phase boundaries of the fused kernel (%globaltimer, ns; CTA 0 / thread 0): [0] start, then one stamp per finished
+	// phase.  Printed by HD_EDIT_FAST_TRACE=1 (a profiling aid: ncu sees the cooperative kernel as one launch).
+	uint32_t n_stamps;
+	uint32_t pad_;
+	unsigned long long stamp_ns[2 * HD_MAX_NODE_LEVELS + 8];
 };
+__device__ __forceinline__ void phase_stamp(DevCounters *ctr) {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	const uint32_t i = ctr->n_stamps;
+	if (i < 2 * HD_MAX_NODE_LEVELS + 8)
+		ctr->stamp_ns[i] = t, ctr->n_stamps = i + 1;
+}
 
 // One BFS level of work items (device arrays, SoA).
 struct LevelView {
@@ -1439,6 +1451,8 @@ __global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_const
 		for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x)
 			reinterpret_cast<uint32_t *>(a.dyn_dev)[i] = reinterpret_cast<const volatile uint32_t *>(a.dyn_host)[i];
 		__syncthreads();
+		if (threadIdx.x == 0)
+			phase_stamp(ctr);
 		if (threadIdx.x < 32)
 			phase_root(g, edits, a.dyn_dev->n_edits, a.iota, a.filled, a.dyn_dev->root, a.lv[0], ctr);
 		__syncthreads();
@@ -1449,7 +1463,7 @@ __global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_const
 			__syncthreads();
 		}
 		if (threadIdx.x == 0)
-			ctr->next_items = l; // first level the whole grid expands
+			ctr->next_items = l, phase_stamp(ctr); // first level the whole grid expands
 	}
 	grid.sync();
 	// ---- stage B (grid): the remaining top-down levels ----
@@ -1457,6 +1471,8 @@ __global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_const
 		phase_down<false>(g, l, a.words, edits, a.filled, a.lv[l], a.lv[l + 1], ctr, &ctr->lvl_items[l + 1], &ctr->lvl_entries[l + 1],
 		                  gtid, gthreads, s_alloc);
 		grid.sync();
+		if (gtid == 0)
+			phase_stamp(ctr);
 	}
 	// ---- stage C (grid): bottom-up over the levels that are worth the grid; then CTA 0 finishes the small top ----
 	if (threadIdx.x == 0) {
@@ -1471,6 +1487,8 @@ __global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_const
 		phase_up(g, l, a.fast_scan, a.words, a.bucket_words, a.locks, edits, a.lv[l], l ? a.lv[l - 1].child_new : nullptr, ctr, s_cand,
 		         gtid, gthreads);
 		grid.sync();
+		if (gtid == 0)
+			phase_stamp(ctr);
 	}
 	if (blockIdx.x != 0)
 		return;
@@ -1479,6 +1497,9 @@ __global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_const
 		         threadIdx.x, blockDim.x);
 		__syncthreads();
 	}
+	if (threadIdx.x == 0)
+		phase_stamp(ctr);
+	__syncthreads();
 	__threadfence();
 	for (uint32_t i = threadIdx.x; i < sizeof(DevCounters) / 4; i += blockDim.x)
 		reinterpret_cast<volatile uint32_t *>(a.ctr_host)[i] = __ldcg(reinterpret_cast<const uint32_t *>(ctr) + i);
@@ -2374,6 +2395,16 @@ static hd_status fast_edit(hd_pool *p, uint32_t root_in, const hd_edit_desc *edi
 	*handled = true;
 	s->last_path = uint32_t(f.mode);
 	*root_out = c.root_out;
+	static const bool trace = getenv("HD_EDIT_FAST_TRACE") && atoi(getenv("HD_EDIT_FAST_TRACE"));
+	if (trace && f.mode == 1 && c.n_stamps) {
+		fprintf(stderr, "[hd] fused edit: %u editors, items per level:", n);
+		for (uint32_t l = 0; l < L; ++l)
+			fprintf(stderr, " %u", c.lvl_items[l]);
+		fprintf(stderr, "\n[hd]   phase ends (us since kernel start; solo top-down | grid top-down... | grid bottom-up... | solo bottom-up):");
+		for (uint32_t i = 1; i < c.n_stamps; ++i)
+			fprintf(stderr, " %.1f", double(c.stamp_ns[i] - c.stamp_ns[0]) * 1e-3);
+		fprintf(stderr, "\n");
+	}
 	if (stats) {
 		memset(stats, 0, sizeof(*stats));
 		for (uint32_t l = 0; l + 1 < L; ++l)

@@ -252,6 +252,7 @@ extern "C" hd_status hd_gc(hd_pool *p, const uint32_t *roots, uint32_t n_roots, 
 	HD_CUDA_TRY(cudaMemsetAsync(G.new_words, 0, g.total_words * sizeof(uint32_t), s));
 	HD_CUDA_TRY(cudaMemsetAsync(G.new_bw, 0, size_t(g.total_buckets) * sizeof(uint32_t), s));
 	G.old_words = p->words, G.old_bw = p->bucket_words;
+	p->tt_invalidate(); // every pointer changes
 	p->words = G.new_words, p->bucket_words = G.new_bw; // upsert_batch_dev appends into the pool's current arrays
 	G.swapped_in = true;
 	for (uint32_t l = L; l-- > 0;) {

@@ -216,6 +216,8 @@ void hd_pool_destroy(hd_pool *p) {
 	cudaFree(p->stage_fetches);
 	cudaFree(p->stage_hits);
 	cudaFree(p->params_dev);
+	cudaFree(p->ray_table);
+	cudaFree(p->tt_entries), cudaFree(p->tt_masks), cudaFree(p->tt_list[0]), cudaFree(p->tt_list[1]), cudaFree(p->tt_count);
 	cudaFree(p->dirty_scratch);
 	cudaFreeHost(p->pick_host);
 	for (int i = 0; i < 2; ++i) {
@@ -262,6 +264,7 @@ hd_status hd_pool_clear(hd_pool *p) {
 	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
 	p->filled.clear();
 	p->root = HD_NULL_NODE;
+	p->tt_invalidate();
 	return HD_OK;
 }
 
@@ -282,6 +285,7 @@ hd_status hd_pool_upload_words(hd_pool *p, uint32_t off, const uint32_t *src, ui
 	HD_CUDA_TRY(cudaSetDevice(p->device));
 	HD_CUDA_TRY(cudaMemcpyAsync(p->words + off, src, size_t(count) * 4, cudaMemcpyHostToDevice, p->stream));
 	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+	p->tt_invalidate(); // arbitrary words were rewritten
 	return HD_OK;
 }
 hd_status hd_pool_read_words(hd_pool *p, uint32_t off, uint32_t *dst, uint32_t count) {

@@ -385,6 +385,7 @@ static hd_status dirty_apply(hd_pool *p, const void *staging_dev, uint64_t packe
 			return cs;
 	}
 	if (h[0]) {
+		p->tt_invalidate(); // ranges from a sender are appends, but nothing here proves it: drop the staged top levels
 		k_dirty_scatter<<<grid, 256, 0, p->stream>>>(p->words, p->bucket_words, p->bucket_synced, p->geo.bucket_shift(), p->geo.total_words,
 		                                           stg, ranges, payload, false, bad_dev);
 		HD_LAUNCH_CHECK();
