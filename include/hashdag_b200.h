@@ -300,6 +300,10 @@ hd_status hd_host_free(void *ptr);
 hd_status hd_pool_used_words(hd_pool *pool, uint64_t *out); /* sum of bucket_words */
 hd_status hd_sync(hd_pool *pool);
 uint64_t hd_kernel_launches(void); /* kernels this library has launched so far (bench gpu_launches) */
+/* Staged top levels of the trace kernel (the compact side table of the node levels next to the root; replaces the pool reads
+ * of trace.frag:132,157-158 there): the root it was built for (HD_NULL_NODE when there is none), how many node levels and
+ * how many nodes it holds.  HD_TRACE_TABLE = 0 / 1 / 2 (never, the default / once a root is traced twice / always) selects the policy. */
+hd_status hd_trace_table_info(hd_pool *pool, uint32_t *root, uint32_t *levels, uint32_t *nodes);
 /* Exhaustive check of the trace kernel's exact-arithmetic shortcuts against the IEEE operations they stand for
  * (trace.frag:83-88, 276-277, 340-356 are written with plain `/` and `sqrt`): the unchecked reciprocal over every float in
  * [2^-51, 2^51), the unchecked square root over every float in [2^-100, 2^100), x / D for every 0 <= x <= D, D in {255, 63, 31,

@@ -301,3 +301,24 @@ def test_degenerate_edits(oracle, hd):
     assert r == NULL
     assert dev.EditBatch(NULL, []) == NULL                                # empty batch: root unchanged
     dev.close()
+
+
+def test_mid_size_batches_one_launch(oracle, hd):
+    """Batches of 33 .. 1000 editors stay on the one-launch path: their lists are longer than 32 entries in the levels
+    next to the root (a warp per (item, child) pair filters them, phase_down_long), shorter below.  Mixed fill / dig / AABB
+    editors, overlapping on purpose so that the order inside a list matters, applied on top of an existing scene."""
+    cfg = abi.default_config(level_count=9, top_level_count=9)
+    vl = cfg.voxel_level
+    base = [abi.terrain(vl)]
+    for n, seed in ((33, 1), (100, 2), (400, 3), (1000, 4)):
+        rng = np.random.default_rng(seed)
+        edits = []
+        for i in range(n):
+            c = tuple(int(v) for v in rng.integers(120, 390, 3))
+            if i % 7 == 3:
+                edits.append(abi.aabb(c, tuple(v + int(rng.integers(4, 50)) for v in c)))
+            else:
+                edits.append(abi.sphere(c, int(rng.integers(4, 60)) ** 2, dig=bool(rng.integers(0, 2))))
+        dev = check_equal(oracle, hd, cfg, base + edits, batches=[1, n])[0]
+        assert dev.last_stats["path"] in ("fused", "graph"), (n, dev.last_stats)
+        dev.close()

@@ -196,6 +196,15 @@ def test_staged_top_levels_equal_the_pool_path(oracle, hd):
     """The staged copy of the top node levels (built once a root is traced for the second time) must not change a single
     output: frames, hit records, iteration counts and F before and after the table exists, across edits (new roots),
     a clear + re-upload, shards, and a DAG too shallow to stage anything."""
+    import os
+    os.environ["HD_TRACE_TABLE"] = "1"     # the library reads it per call; off by default (it loses on cfg2, DESIGN 3.1)
+    try:
+        _staged_top_levels(oracle, hd)
+    finally:
+        os.environ.pop("HD_TRACE_TABLE", None)
+
+
+def _staged_top_levels(oracle, hd):
     cfg = abi.default_config(level_count=10, top_level_count=9)
     opool = oracle.pool(cfg)
     roots = [opool.edit_batch(NULL, [abi.terrain(cfg.voxel_level)] + abi.random_spheres(30, cfg.voxel_level, seed=2, rmin=8, rmax=80))]
@@ -211,13 +220,16 @@ def test_staged_top_levels_equal_the_pool_path(oracle, hd):
                     P = abi.camera_params(cfg, root, *cam[:3], W, H, color_root=(1 << 30) | 0x4080C0, lod=cam[3])
                     exp = oracle.trace_frame(opool.words_ptr, P)
                     got = dev.Trace(P, want=("rgba8", "hits", "iters", "fetches"))
-                    for key in ("rgba8", "hits", "iters", "fetches"):
+                    for key in ("rgba8", "hits", "iters"):
                         assert np.array_equal(got[key], exp[key]), (rnd, root, k, cam, key)
+                    assert int(got["fetches"].sum(dtype=np.uint64)) == exp["fetches"], (rnd, root, k, cam, "F")
                     lean = dev.Trace(P, want=("rgba8",))
                     assert np.array_equal(lean["rgba8"], exp["rgba8"]), (rnd, root, k, cam, "lean")
                     sh = dev.Trace(P, want=("rgba8",), shard=(64, 64, 1, 2))
                     ref_sh = oracle_shard(exp["rgba8"], P, (64, 64, 1, 2), dev)
                     assert np.array_equal(sh["rgba8"], ref_sh), (rnd, root, k, cam, "shard")
+            troot, tlevels, tnodes = dev.TraceTableInfo()   # the last frames of this root really read the table
+            assert troot == root and 1 <= tlevels <= cfg.node_levels - 2 and tnodes > tlevels, (troot, tlevels, tnodes)
         dev.Clear()                        # invalidates the table; the same pointers come back with the re-upload
         dev.UploadFrom(opool)
     dev.close()

@@ -68,7 +68,7 @@ SYMBOLS = [
     "hd_pool_load", "hd_gc", "hd_trace_submit", "hd_trace_collect", "hd_beam_dev",
     "hd_trace_with_beam_dev", "hd_trace_with_beam", "hd_color_config", "hd_color_root", "hd_color_leaf_level",
     "hd_color_sizes", "hd_color_read", "hd_edit_color", "hd_edit_last_path",
-    "hd_tile_shard_locate", "hd_pool_read_subtree", "hd_host_alloc", "hd_host_free", "hd_selftest_exact_arith",
+    "hd_tile_shard_locate", "hd_pool_read_subtree", "hd_host_alloc", "hd_host_free", "hd_selftest_exact_arith", "hd_trace_table_info",
 ]
 
 
@@ -151,6 +151,7 @@ def lib():
     L.hd_host_free.argtypes = [vp]
     L.hd_kernel_launches.restype = u64
     L.hd_selftest_exact_arith.argtypes = [ci, C.POINTER(u64)]
+    L.hd_trace_table_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
     _lib = L
     return L
 
@@ -441,6 +442,12 @@ class DAGNodePool:
         else:
             _check(self._L.hd_trace_tiles(self._h, C.byref(params), C.byref(shard), C.byref(o)))
         return res
+
+    def TraceTableInfo(self):
+        """(root, node levels, nodes) of the staged top levels the trace kernel currently holds; root == NULL: none."""
+        r, l, n = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(self._L.hd_trace_table_info(self._h, C.byref(r), C.byref(l), C.byref(n)))
+        return int(r.value), int(l.value), int(n.value)
 
     def TraceDev(self, params, rgba8=0, hits=0, iters=0, fetches=0, shard=None):
         """Enqueue one frame with DEVICE output pointers (ints, e.g. torch.Tensor.data_ptr()); no synchronisation."""

@@ -50,6 +50,7 @@ struct DevCounters {
 	// low-latency path (one CUDA graph, no host round trips): item / list-entry counts of every level stay on the device
 	uint32_t lvl_items[HD_MAX_NODE_LEVELS];
 	uint32_t lvl_entries[HD_MAX_NODE_LEVELS];
+	uint32_t lvl_long[HD_MAX_NODE_LEVELS]; // fused kernel: some item of the level carries a list longer than 32 entries
 	// phase boundaries of the fused kernel (%globaltimer, ns; CTA 0 / thread 0): [0] start, then one stamp per finished
 	// phase.  Printed by HD_EDIT_FAST_TRACE=1 (a profiling aid: ncu sees the cooperative kernel as one launch).
 	uint32_t n_stamps;
@@ -289,6 +290,38 @@ __device__ __forceinline__ bool alloc_item(DevCounters *ctr, uint32_t *items_ctr
 	return want;
 }
 
+// The same reservation per WARP (ballot, warp scan, one pair of atomics by lane 0): no CTA barrier, so the warps of a CTA run
+// on independently and their load chains overlap.  For the one-launch path, whose levels hold at most 2^19 items (tens of
+// thousands of atomics, not millions).  Must be called by all 32 lanes.
+__device__ __forceinline__ bool alloc_item_warp(DevCounters *ctr, uint32_t *items_ctr, uint32_t *entries_ctr, bool want,
+                                                uint32_t count, uint32_t cap, uint32_t cap_entries, uint32_t &item,
+                                                uint32_t &entry_off) {
+	const uint32_t full = 0xFFFFFFFFu, lane = threadIdx.x & 31u;
+	const uint32_t wants = __ballot_sync(full, want);
+	if (wants == 0u)
+		return false;
+	uint32_t c = want ? count : 0u, scan = c;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t v = __shfl_up_sync(full, scan, d);
+		if (lane >= uint32_t(d))
+			scan += v;
+	}
+	uint32_t bi = 0, be = 0;
+	if (lane == 31u) {
+		bi = atomicAdd(items_ctr, uint32_t(__popc(wants)));
+		be = atomicAdd(entries_ctr, scan);
+	}
+	bi = __shfl_sync(full, bi, 31), be = __shfl_sync(full, be, 31);
+	item = bi + __popc(wants & ((1u << lane) - 1u));
+	entry_off = be + scan - c;
+	if (want && (item >= cap || entry_off + count > cap_entries)) {
+		ctr->error = 1;
+		return false;
+	}
+	return want;
+}
+
 // ---- warp-cooperative filtering for long lists (all 32 lanes pass the same arguments) -------------------------------
 struct WarpFiltered {
 	uint32_t cur, count, start;
@@ -376,6 +409,7 @@ __device__ __forceinline__ void phase_root(const Geometry &g, const hd_edit_desc
 	ctr->next_entries = r.x + r.y;
 	ctr->lvl_items[0] = 1;
 	ctr->lvl_entries[0] = r.x + r.y;
+	ctr->lvl_long[0] = r.y > 32u ? 1u : 0u;
 	out.cur[0] = f.cur;
 	out.pos[0] = 0;
 	out.parent[0] = 0xFFFFFFFFu;
@@ -622,7 +656,9 @@ __global__ void __launch_bounds__(kBlock) k_down_long(Geometry g, uint32_t level
 // grid from a known item count, a grid-stride loop over the device-resident count on the low-latency path).
 // (tid0, nthreads) = this thread's index among, and the number of, the threads that share the level: the whole grid, or
 // one CTA when the fused kernel walks a small level alone.
-template <bool kTerrain>
+// kWarpAlloc (fused kernel): queue slots are reserved per warp (alloc_item_warp) and lists longer than 32 entries are left
+// to phase_down_long; otherwise per CTA, and `in.n_dev` set (the CUDA-graph variant) means this thread walks long lists itself.
+template <bool kTerrain, bool kWarpAlloc = false>
 __device__ __forceinline__ void phase_down(const Geometry &g, uint32_t level /* of `in` */,
                                            const uint32_t *__restrict__ words, const hd_edit_desc *__restrict__ edits,
                                            const uint32_t *__restrict__ filled, const LevelView &in, const LevelView &out,
@@ -630,7 +666,9 @@ __device__ __forceinline__ void phase_down(const Geometry &g, uint32_t level /* 
                                            uint32_t nthreads, uint32_t *s_alloc) {
 	const uint32_t n8 = in.count() * 8u;
 	const uint32_t bits = g.voxel_level() - (level + 1u);
-	for (uint32_t t = tid0; t - threadIdx.x < n8; t += nthreads) { // whole CTAs iterate together (alloc_item synchronises)
+	const bool serial_long = !kWarpAlloc && in.n_dev != nullptr;
+	// whole CTAs (alloc_item synchronises) or whole warps (alloc_item_warp shuffles) iterate together
+	for (uint32_t t = tid0; t - (kWarpAlloc ? (threadIdx.x & 31u) : threadIdx.x) < n8; t += nthreads) {
 		const uint32_t item = t >> 3, c = t & 7u;
 		const bool valid = t < n8;
 		Filtered f{kNull, 0u, 0u, 0u};
@@ -650,14 +688,16 @@ __device__ __forceinline__ void phase_down(const Geometry &g, uint32_t level /* 
 			len = in.list_len[item];
 			// lists longer than 32: k_down_long on the host-driven path; on the one-launch path (device-resident counts)
 			// this thread walks them itself — they only occur in the few levels next to the root
-			if (len <= 32u || in.n_dev)
+			if (len <= 32u || serial_long)
 				f = filter_list<kTerrain>(edits, list, len, bits, x, y, z, child, filled[level + 1u]);
 		}
 		uint32_t slot, entry_off;
-		const bool made = alloc_item(ctr, items_ctr, entries_ctr, valid && f.count != 0, f.count, out.cap, out.cap_entries,
-		                             slot, entry_off, s_alloc);
-		if (!valid || (len > 32u && !in.n_dev))
-			continue; // long lists: k_down_long
+		const bool made = kWarpAlloc ? alloc_item_warp(ctr, items_ctr, entries_ctr, valid && f.count != 0, f.count, out.cap,
+		                                               out.cap_entries, slot, entry_off)
+		                             : alloc_item(ctr, items_ctr, entries_ctr, valid && f.count != 0, f.count, out.cap,
+		                                          out.cap_entries, slot, entry_off, s_alloc);
+		if (!valid || (len > 32u && !serial_long))
+			continue; // long lists: k_down_long / phase_down_long
 		if (made) {
 			out.cur[slot] = f.cur;
 			out.pos[slot] = pack_pos(x, y, z);
@@ -671,6 +711,84 @@ __device__ __forceinline__ void phase_down(const Geometry &g, uint32_t level /* 
 		}
 	}
 }
+// Fused kernel: the (item, child) pairs whose parent carries a list longer than 32 entries — the levels next to the root of
+// a batch of dozens to a thousand editors.  A warp per pair filters the list cooperatively (warp_filter_*); walking such
+// lists with one thread per pair made the top levels of a 100-editor batch 0.45 of its 1.15 ms.  (w0, nw) = this warp's
+// index among, and the number of, the warps sharing the level.  Small levels stride over pairs; on large levels a warp
+// checks 32 items' list lengths at a time and only visits the long ones.
+__device__ __forceinline__ void phase_down_long(const Geometry &g, uint32_t level, const uint32_t *__restrict__ words,
+                                                const hd_edit_desc *__restrict__ edits, const uint32_t *__restrict__ filled,
+                                                const LevelView &in, const LevelView &out, DevCounters *ctr, uint32_t *items_ctr,
+                                                uint32_t *entries_ctr, uint32_t *long_flag, uint32_t w0, uint32_t nw) {
+	const uint32_t lane = threadIdx.x & 31u, full = 0xFFFFFFFFu;
+	const uint32_t n = in.count(), bits = g.voxel_level() - (level + 1u), fp = filled[level + 1u];
+	auto do_pair = [&](uint32_t item, uint32_t c, uint32_t len) {
+		const uint32_t cur = in.cur[item];
+		uint32_t child = kNull;
+		if (cur != kNull) {
+			const uint32_t mask = words[cur];
+			if (mask >> c & 1u)
+				child = words[cur + 1u + __popc(mask & ((1u << c) - 1u))];
+		}
+		uint32_t x, y, z;
+		unpack_pos(in.pos[item], x, y, z);
+		x = (x << 1) | (c & 1u), y = (y << 1) | ((c >> 1) & 1u), z = (z << 1) | ((c >> 2) & 1u);
+		const uint32_t *list = in.lists + in.list_off[item];
+		const WarpFiltered f = warp_filter_count(edits, list, len, bits, x, y, z, child, fp);
+		uint32_t result = f.cur;
+		if (f.count) {
+			uint32_t entry_off = 0;
+			if (lane == 0)
+				entry_off = atomicAdd(entries_ctr, f.count);
+			entry_off = __shfl_sync(full, entry_off, 0);
+			if (entry_off + f.count > out.cap_entries) {
+				if (lane == 0)
+					ctr->error = 1;
+				return;
+			}
+			const uint2 r = warp_filter_write(edits, list, len, bits, x, y, z, f, fp, out.lists + entry_off);
+			if (r.y) {
+				if (lane == 0) {
+					const uint32_t slot = atomicAdd(items_ctr, 1u);
+					if (slot >= out.cap)
+						ctr->error = 1;
+					else {
+						out.cur[slot] = f.cur;
+						out.pos[slot] = pack_pos(x, y, z);
+						out.parent[slot] = (item << 3) | c;
+						out.list_off[slot] = entry_off + r.x;
+						out.list_len[slot] = r.y;
+						if (r.y > 32u)
+							*long_flag = 1u;
+					}
+				}
+				result = kPending;
+			}
+		}
+		if (lane == 0)
+			in.child_new[size_t(item) * 8u + c] = result;
+	};
+	if (n * 8u <= nw * 8u) { // few pairs: one warp each
+		for (uint32_t w = w0; w < n * 8u; w += nw) {
+			const uint32_t len = in.list_len[w >> 3];
+			if (len > 32u)
+				do_pair(w >> 3, w & 7u, len);
+		}
+	} else { // many items, few of them long: 32 list lengths per trip
+		for (uint32_t base = w0 * 32u; base < n; base += nw * 32u) {
+			const uint32_t mine = base + lane < n ? in.list_len[base + lane] : 0u;
+			uint32_t todo = __ballot_sync(full, mine > 32u);
+			while (todo) {
+				const uint32_t k = __ffs(todo) - 1u;
+				todo &= todo - 1u;
+				const uint32_t len = __shfl_sync(full, mine, k);
+				for (uint32_t c = 0; c < 8u; ++c)
+					do_pair(base + k, c, len);
+			}
+		}
+	}
+}
+
 template <bool kTerrain>
 __global__ void __launch_bounds__(kBlock) k_down(Geometry g, uint32_t level, const uint32_t *__restrict__ words,
                                                  const hd_edit_desc *__restrict__ edits,
@@ -1457,9 +1575,10 @@ __global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_const
 			phase_root(g, edits, a.dyn_dev->n_edits, a.iota, a.filled, a.dyn_dev->root, a.lv[0], ctr);
 		__syncthreads();
 		uint32_t l = 0;
-		for (; l + 1 < L && items[l] <= kSoloDown; ++l) {
-			phase_down<false>(g, l, a.words, edits, a.filled, a.lv[l], a.lv[l + 1], ctr, &ctr->lvl_items[l + 1],
-			                  &ctr->lvl_entries[l + 1], threadIdx.x, blockDim.x, s_alloc);
+		// (levels whose lists are longer than 32 entries go to the grid: a warp per (item, child) pair)
+		for (; l + 1 < L && items[l] <= kSoloDown && *(volatile uint32_t *)&ctr->lvl_long[l] == 0u; ++l) {
+			phase_down<false, true>(g, l, a.words, edits, a.filled, a.lv[l], a.lv[l + 1], ctr, &ctr->lvl_items[l + 1],
+			                        &ctr->lvl_entries[l + 1], threadIdx.x, blockDim.x, s_alloc);
 			__syncthreads();
 		}
 		if (threadIdx.x == 0)
@@ -1468,8 +1587,11 @@ __global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_const
 	grid.sync();
 	// ---- stage B (grid): the remaining top-down levels ----
 	for (uint32_t l = *(volatile uint32_t *)&ctr->next_items; l + 1 < L; ++l) {
-		phase_down<false>(g, l, a.words, edits, a.filled, a.lv[l], a.lv[l + 1], ctr, &ctr->lvl_items[l + 1], &ctr->lvl_entries[l + 1],
-		                  gtid, gthreads, s_alloc);
+		phase_down<false, true>(g, l, a.words, edits, a.filled, a.lv[l], a.lv[l + 1], ctr, &ctr->lvl_items[l + 1],
+		                        &ctr->lvl_entries[l + 1], gtid, gthreads, s_alloc);
+		if (*(volatile uint32_t *)&ctr->lvl_long[l])
+			phase_down_long(g, l, a.words, edits, a.filled, a.lv[l], a.lv[l + 1], ctr, &ctr->lvl_items[l + 1],
+			                &ctr->lvl_entries[l + 1], &ctr->lvl_long[l + 1], gtid >> 5, gthreads >> 5);
 		grid.sync();
 		if (gtid == 0)
 			phase_stamp(ctr);
