@@ -151,12 +151,10 @@ __global__ void k_croot(ColorEdit e, uint32_t geom_root, uint32_t oct_root, CIte
 }
 
 // thread per (inner item at `level`, child): VBREditorWrapper::EditNode for levels <= leaf_level (VBREditor.hpp:37-59)
-__global__ void __launch_bounds__(kCB) k_cdown(ColorEdit e, uint32_t level, const uint32_t *__restrict__ words,
-                                               const uint32_t *__restrict__ cnodes, CItems in, CItems inner, CItems leaf,
-                                               uint32_t *counts) {
-	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, item = t >> 3, c = t & 7u;
-	if (item >= in.count())
-		return;
+__device__ __forceinline__ void cdown_pair(const ColorEdit &e, uint32_t level, const uint32_t *__restrict__ words,
+                                           const uint32_t *__restrict__ cnodes, const CItems &in, const CItems &inner,
+                                           const CItems &leaf, uint32_t *counts, uint32_t t) {
+	const uint32_t item = t >> 3, c = t & 7u;
 	const uint32_t g = in.geom[item];
 	uint32_t child = kNull;
 	if (g != kNull) {
@@ -174,7 +172,7 @@ __global__ void __launch_bounds__(kCB) k_cdown(ColorEdit e, uint32_t level, cons
 		in.child[size_t(item) * 8u + c] = res;
 		return;
 	}
-	CItems &dst = k == 1 ? inner : leaf;
+	const CItems &dst = k == 1 ? inner : leaf;
 	const uint32_t slot = atomicAdd(&counts[k - 1], 1u);
 	if (slot >= dst.cap) {
 		counts[3] = 1;
@@ -186,13 +184,53 @@ __global__ void __launch_bounds__(kCB) k_cdown(ColorEdit e, uint32_t level, cons
 	dst.parent[slot] = (item << 3) | c;
 	in.child[size_t(item) * 8u + c] = kCPending;
 }
+__global__ void __launch_bounds__(kCB) k_cdown(ColorEdit e, uint32_t level, const uint32_t *__restrict__ words,
+                                               const uint32_t *__restrict__ cnodes, CItems in, CItems inner, CItems leaf,
+                                               uint32_t *counts) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if ((t >> 3) < in.count())
+		cdown_pair(e, level, words, cnodes, in, inner, leaf, counts, t);
+}
+
+// The whole octree descent of a brush-sized edit in ONE launch: root classification, then the levels one after the other
+// inside a single CTA (a brush touches a handful of octree nodes per level; a launch per level was a quarter of the
+// colour pass's launches).  lvl_counts block l = what produced level l: [0] inner items, [1] leaves, [3] overflow.
+struct CLevels {
+	CItems lv[HD_MAX_NODE_LEVELS + 1];
+};
+constexpr int kOctThreads = 1024;
+__global__ void __launch_bounds__(kOctThreads) k_cdown_all(ColorEdit e, uint32_t geom_root, uint32_t oct_root,
+                                                           const uint32_t *__restrict__ words, const uint32_t *cnodes,
+                                                           const __grid_constant__ CLevels L, CItems leaf, uint32_t *lvl_counts,
+                                                           uint32_t *root_out) {
+	const uint32_t LL = e.leaf_level;
+	if (threadIdx.x == 0) {
+		uint32_t res = oct_root;
+		const int k = classify_oct(e, 0, 0, 0, 0, geom_root, oct_root, res);
+		if (k == 0)
+			*root_out = res;
+		else {
+			const CItems &dst = k == 1 ? L.lv[0] : leaf;
+			lvl_counts[k - 1] = 1;
+			dst.geom[0] = geom_root, dst.oct[0] = oct_root, dst.pos[0] = 0, dst.parent[0] = 0xFFFFFFFFu;
+		}
+	}
+	__threadfence_block();
+	__syncthreads();
+	for (uint32_t l = 0; l < LL; ++l) {
+		const uint32_t n = min(*(volatile const uint32_t *)(lvl_counts + 4u * l), L.lv[l].cap);
+		if (n == 0u)
+			break;
+		for (uint32_t t = threadIdx.x; t < n * 8u; t += blockDim.x)
+			cdown_pair(e, l, words, cnodes, L.lv[l], L.lv[l + 1u], leaf, lvl_counts + 4u * (l + 1u), t);
+		__threadfence_block();
+		__syncthreads();
+	}
+}
 
 // JoinNode above the leaf level: DAGColorPool::SetNode (DAGColorPool.hpp:147-163).  Thread per inner item.
-__global__ void __launch_bounds__(kCB) k_cup(CItems it, uint32_t *cnodes, uint32_t *ctr, uint64_t node_cap, uint32_t *parent_child,
-                                             uint32_t *root_out) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= it.count())
-		return;
+__device__ __forceinline__ void cup_item(const CItems &it, uint32_t *cnodes, uint32_t *ctr, uint64_t node_cap,
+                                         uint32_t *parent_child, uint32_t *root_out, uint32_t i) {
 	uint32_t ch[8];
 	bool all_null = true, all_same = true;
 	for (int c = 0; c < 8; ++c) {
@@ -230,6 +268,63 @@ __global__ void __launch_bounds__(kCB) k_cup(CItems it, uint32_t *cnodes, uint32
 		*root_out = res;
 	else
 		parent_child[par] = res;
+}
+__global__ void __launch_bounds__(kCB) k_cup(CItems it, uint32_t *cnodes, uint32_t *ctr, uint64_t node_cap, uint32_t *parent_child,
+                                             uint32_t *root_out) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < it.count())
+		cup_item(it, cnodes, ctr, node_cap, parent_child, root_out, i);
+}
+// every inner level from `top` - 1 down to the root in one launch (one CTA; item counts are host-known by now)
+__global__ void __launch_bounds__(kOctThreads) k_cup_all(const __grid_constant__ CLevels L, uint32_t top, uint32_t *cnodes,
+                                                         uint32_t *ctr, uint64_t node_cap, uint32_t *root_out) {
+	for (uint32_t l = top; l-- > 0u;) {
+		const uint32_t n = L.lv[l].n;
+		for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+			cup_item(L.lv[l], cnodes, ctr, node_cap, l ? L.lv[l - 1u].child : nullptr, root_out, i);
+		__threadfence_block();
+		__syncthreads();
+	}
+}
+
+// Exclusive prefix sums of TWO arrays of up to 256 K entries in one launch of one CTA (the block path's run and weight-bit
+// counts: 4 096 blocks per colour leaf, a handful of leaves per brush).  Larger inputs take exclusive_scan.
+constexpr uint32_t kSmallScan = 1u << 18;
+__global__ void __launch_bounds__(1024) k_scan2_small(const uint32_t *__restrict__ in0, uint32_t *out0,
+                                                      const uint32_t *__restrict__ in1, uint32_t *out1, uint32_t n) {
+	__shared__ uint32_t s_warp[2][32];
+	const uint32_t per = (n + 1023u) / 1024u, lo = min(threadIdx.x * per, n), hi = min(lo + per, n);
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	uint32_t sum[2] = {0u, 0u};
+	for (uint32_t i = lo; i < hi; ++i)
+		sum[0] += in0[i], sum[1] += in1[i];
+	uint32_t incl[2] = {sum[0], sum[1]};
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, incl[0], d), b = __shfl_up_sync(0xFFFFFFFFu, incl[1], d);
+		if (lane >= uint32_t(d))
+			incl[0] += a, incl[1] += b;
+	}
+	if (lane == 31u)
+		s_warp[0][warp] = incl[0], s_warp[1][warp] = incl[1];
+	__syncthreads();
+	if (warp == 0u) {
+		uint32_t a = s_warp[0][lane], b = s_warp[1][lane];
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, a, d), y = __shfl_up_sync(0xFFFFFFFFu, b, d);
+			if (lane >= uint32_t(d))
+				a += x, b += y;
+		}
+		s_warp[0][lane] = a - s_warp[0][lane], s_warp[1][lane] = b - s_warp[1][lane]; // exclusive over the warps
+	}
+	__syncthreads();
+	uint32_t run0 = s_warp[0][warp] + incl[0] - sum[0], run1 = s_warp[1][warp] + incl[1] - sum[1];
+	for (uint32_t i = lo; i < hi; ++i) { // in == out is allowed: read before write
+		const uint32_t a = in0[i], b = in1[i];
+		out0[i] = run0, out1[i] = run1;
+		run0 += a, run1 += b;
+	}
 }
 
 // ---- leaf part: per-voxel colour, then canonical VBR encoding -------------------------------------------------------
@@ -359,22 +454,23 @@ __global__ void __launch_bounds__(256) k_scan_add(uint32_t *out, const uint32_t 
 			out[i + k] += o;
 }
 
-hd_status exclusive_scan(hd_pool *p, const uint32_t *in, uint32_t *out, uint64_t n) {
+hd_status exclusive_scan(hd_pool *p, const uint32_t *in, uint32_t *out, uint64_t n, cudaStream_t stream) {
 	if (n == 0)
 		return HD_OK;
+	cudaStream_t st = stream ? stream : p->stream;
 	const uint64_t blocks = (n + 1023) / 1024;
 	uint32_t *sums = nullptr;
-	HD_CUDA_TRY(cudaMallocAsync(&sums, std::max<uint64_t>(blocks, 1) * 4, p->stream));
-	k_scan_block<<<uint32_t(blocks), 256, 0, p->stream>>>(in, out, sums, n);
+	HD_CUDA_TRY(cudaMallocAsync(&sums, std::max<uint64_t>(blocks, 1) * 4, st));
+	k_scan_block<<<uint32_t(blocks), 256, 0, st>>>(in, out, sums, n);
 	HD_LAUNCH_CHECK();
 	if (blocks > 1) {
-		hd_status s = exclusive_scan(p, sums, sums, blocks);
+		hd_status s = exclusive_scan(p, sums, sums, blocks, st);
 		if (s != HD_OK)
 			return s;
-		k_scan_add<<<uint32_t(blocks), 256, 0, p->stream>>>(out, sums, n);
+		k_scan_add<<<uint32_t(blocks), 256, 0, st>>>(out, sums, n);
 		HD_LAUNCH_CHECK();
 	}
-	HD_CUDA_TRY(cudaFreeAsync(sums, p->stream));
+	HD_CUDA_TRY(cudaFreeAsync(sums, st));
 	return HD_OK;
 }
 
@@ -798,6 +894,8 @@ hd_status ensure_color_storage(hd_pool *p, uint64_t node_words, uint64_t leaf_wo
 		uint32_t *nb = nullptr;
 		HD_CUDA_TRY(cudaMalloc(&nb, ncap * 4));
 		HD_CUDA_TRY(cudaMemsetAsync(nb, 0, ncap * 4, s));
+		if (p->color_stream) // kernels of a colour pass running beside a rebuild may still read (or have written) the old buffer
+			HD_CUDA_TRY(cudaStreamSynchronize(p->color_stream));
 		if (buf && used)
 			HD_CUDA_TRY(cudaMemcpyAsync(nb, buf, used * 4, cudaMemcpyDeviceToDevice, s));
 		HD_CUDA_TRY(cudaStreamSynchronize(s));
@@ -875,7 +973,7 @@ hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, 
 		return HD_ERR_INVALID;
 	}
 	HD_CUDA_TRY(cudaSetDevice(p->device));
-	cudaStream_t s = p->stream;
+	cudaStream_t s = p->stream; // replaced by the colour stream below when the geometry edit runs beside this pass
 	const Geometry &g = p->geo;
 	ColorEdit e{};
 	e.d = *edit, e.rgb8 = rgb8 & 0xFFFFFFu, e.paint = paint ? 1u : 0u;
@@ -891,13 +989,48 @@ hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, 
 	// ---- geometry first (SphereEditor<kPaint> leaves the voxels alone, main.cpp:133-136): the node pool is append-only, so
 	// a failure here (bucket overflow, CUDA error) leaves both pools exactly as they were, and the colour pass below still
 	// sees the OLD geometry under root_in.  Only the in-place rewrite of leaf chunks cannot be rolled back once it starts.
+	// Round 2b: the one-launch rebuild is only ENQUEUED here (fast_edit_begin) and this pass runs beside it on a stream of
+	// its own — it reads the old geometry, which the rebuild never touches — up to its first irreversible write, where
+	// finish_geometry() waits for the rebuild and gives up (both pools untouched) if it failed.
 	uint32_t new_root = root_in;
+	bool geometry_in_flight = false, geometry_done = paint != 0u;
 	if (!paint) {
-		st = hd_edit_batch(p, root_in, edit, 1, &new_root, stats);
-		if (st != HD_OK)
-			return st;
+		static const bool overlap = !(getenv("HD_COLOR_OVERLAP") && atoi(getenv("HD_COLOR_OVERLAP")) == 0);
+		if (overlap) {
+			st = edit_prepare(p);
+			if (st == HD_OK)
+				st = fast_edit_begin(p, root_in, edit, 1, &geometry_in_flight, true);
+			if (st != HD_OK)
+				return st;
+		}
+		if (geometry_in_flight) {
+			if (!p->color_stream)
+				HD_CUDA_TRY(cudaStreamCreateWithFlags(&p->color_stream, cudaStreamNonBlocking));
+			s = p->color_stream;
+		} else {
+			st = hd_edit_batch(p, root_in, edit, 1, &new_root, stats);
+			if (st != HD_OK)
+				return st;
+			geometry_done = true;
+		}
 	} else if (stats)
 		memset(stats, 0, sizeof(*stats));
+	auto finish_geometry = [&]() -> hd_status {
+		if (geometry_done)
+			return HD_OK;
+		geometry_done = true;
+		bool handled = false;
+		hd_status gs = fast_edit_end(p, &new_root, stats, &handled);
+		geometry_in_flight = false;
+		if (gs == HD_OK && !handled) // a work queue was too small (nothing written): the general path redoes the edit
+			gs = hd_edit_batch(p, root_in, edit, 1, &new_root, stats);
+		return gs;
+	};
+	// whatever happens below, the rebuild must not be left in flight behind the caller's back
+	ScopeExit wait_geometry{[&]() {
+		if (geometry_in_flight)
+			cudaStreamSynchronize(p->stream);
+	}};
 
 	// ---- colour pass over the OLD geometry (node memory is immutable) ----
 	std::vector<CLevel> inner(LL + 1);
@@ -956,11 +1089,11 @@ hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, 
 		}
 		leaf.init_from(q, kLeafCap, false, s);
 		leaf.v.n_dev = lvl_counts + 4 * LL + 1;
-		k_croot<<<1, 32, 0, s>>>(e, root_in, col_root_in, inner[0].v, leaf.v, lvl_counts, root_dev);
-		HD_LAUNCH_CHECK();
-		for (uint32_t l = 0; l < LL; ++l) {
-			k_cdown<<<cblocks(uint64_t(cap_of(l)) * 8), kCB, 0, s>>>(e, l, p->words, p->color_nodes, inner[l].v, inner[l + 1].v, leaf.v,
-			                                                       lvl_counts + 4 * (l + 1));
+		{
+			CLevels all{};
+			for (uint32_t l = 0; l <= LL; ++l)
+				all.lv[l] = inner[l].v;
+			k_cdown_all<<<1, kOctThreads, 0, s>>>(e, root_in, col_root_in, p->words, p->color_nodes, all, leaf.v, lvl_counts, root_dev);
 			HD_LAUNCH_CHECK();
 		}
 		std::vector<uint32_t> hcs(4 * (LL + 2));
@@ -1040,30 +1173,31 @@ hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, 
 			uint32_t *list = nullptr, *list_count = nullptr, *rscan = nullptr, *wscan = nullptr, *chunk_idx = nullptr, *colors = nullptr;
 			uint8_t *bw = nullptr;
 			unsigned long long *total = nullptr;
+			// one stream-ordered allocation for the per-block arrays (sixteen of them cost more host time than the kernels run)
+			char *block_arena = nullptr;
 			ScopeExit free_batch{[&]() {
-				void *ptrs[] = {B.key, B.first_c, B.last_c, B.first_b, B.last_b, B.runs, B.bits, B.slot, B.start, list, list_count,
-				                rscan, wscan, chunk_idx, colors, bw, total};
-				for (void *q : ptrs)
-					if (q)
-						cudaFreeAsync(q, s);
+				if (block_arena)
+					cudaFreeAsync(block_arena, s);
+				if (colors)
+					cudaFreeAsync(colors, s);
+				if (bw)
+					cudaFreeAsync(bw, s);
 			}};
-			HD_CUDA_TRY(cmalloc(&B.key, nb, s));
-			HD_CUDA_TRY(cmalloc(&B.first_c, nb, s));
-			HD_CUDA_TRY(cmalloc(&B.last_c, nb, s));
-			HD_CUDA_TRY(cmalloc(&B.first_b, nb, s));
-			HD_CUDA_TRY(cmalloc(&B.last_b, nb, s));
-			HD_CUDA_TRY(cmalloc(&B.runs, nb, s));
-			HD_CUDA_TRY(cmalloc(&B.bits, nb, s));
-			HD_CUDA_TRY(cmalloc(&B.slot, nb, s));
-			HD_CUDA_TRY(cmalloc(&B.start, nb, s));
-			HD_CUDA_TRY(cmalloc(&list, nb, s));
-			HD_CUDA_TRY(cmalloc(&list_count, 1, s));
-			HD_CUDA_TRY(cmalloc(&rscan, nb, s));
-			HD_CUDA_TRY(cmalloc(&wscan, nb, s));
-			HD_CUDA_TRY(cmalloc(&chunk_idx, nl, s));
-			HD_CUDA_TRY(cmalloc(&total, 1, s));
-			HD_CUDA_TRY(cudaMemsetAsync(list_count, 0, 4, s));
-			HD_CUDA_TRY(cudaMemsetAsync(total, 0, 8, s));
+			{
+				const size_t w4 = (size_t(nb) * 4 + 255) & ~size_t(255), w1 = (size_t(nb) + 255) & ~size_t(255);
+				const size_t bytes = 10 * w4 + 3 * w1 + ((size_t(nl) * 4 + 255) & ~size_t(255)) + 512;
+				HD_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&block_arena), bytes, s));
+				char *q = block_arena;
+				auto take4 = [&]() { uint32_t *r = reinterpret_cast<uint32_t *>(q); q += w4; return r; };
+				auto take1 = [&]() { uint8_t *r = reinterpret_cast<uint8_t *>(q); q += w1; return r; };
+				B.key = take4(), B.first_c = take4(), B.last_c = take4(), B.runs = take4(), B.bits = take4(), B.slot = take4();
+				list = take4(), rscan = take4(), wscan = take4();
+				B.first_b = take1(), B.last_b = take1(), B.start = take1();
+				chunk_idx = reinterpret_cast<uint32_t *>(q), q += (size_t(nl) * 4 + 255) & ~size_t(255);
+				total = reinterpret_cast<unsigned long long *>(q), q += 256;
+				list_count = reinterpret_cast<uint32_t *>(q);
+				HD_CUDA_TRY(cudaMemsetAsync(total, 0, 512, s)); // total and list_count
+			}
 			k_cblock<<<cblocks(nb), kCB, 0, s>>>(e, p->words, p->color_leaves, leaf.v, first, nl, sbits, B, list, list_count);
 			HD_LAUNCH_CHECK();
 			uint32_t n_listed = 0;
@@ -1081,17 +1215,24 @@ hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, 
 			}
 			k_block_flags<<<cblocks(nb), kCB, 0, s>>>(nb, sbits, B);
 			HD_LAUNCH_CHECK();
-			st = exclusive_scan(p, B.runs, rscan, nb);
-			if (st == HD_OK)
-				st = exclusive_scan(p, B.bits, wscan, nb);
-			if (st != HD_OK)
-				return st;
+			if (nb <= kSmallScan) {
+				k_scan2_small<<<1, 1024, 0, s>>>(B.runs, rscan, B.bits, wscan, nb);
+				HD_LAUNCH_CHECK();
+			} else {
+				st = exclusive_scan(p, B.runs, rscan, nb, s);
+				if (st == HD_OK)
+					st = exclusive_scan(p, B.bits, wscan, nb, s);
+				if (st != HD_OK)
+					return st;
+			}
 			unsigned long long need = 0;
 			k_leaf_size<<<cblocks(nl), kCB, 0, s>>>(leaf.v, first, nl, sbits, bbits, B.runs, rscan, B.bits, wscan, p->color_leaves, total);
 			HD_LAUNCH_CHECK();
 			HD_CUDA_TRY(cudaMemcpyAsync(&need, total, 8, cudaMemcpyDeviceToHost, s));
 			HD_CUDA_TRY(cudaStreamSynchronize(s));
-			st = ensure_color_storage(p, p->color_node_words, p->color_leaf_words + need);
+			st = finish_geometry(); // everything up to here only filled scratch arrays; chunks are rewritten in place from here on
+			if (st == HD_OK)
+				st = ensure_color_storage(p, p->color_node_words, p->color_leaf_words + need);
 			if (st != HD_OK)
 				return st;
 			k_leaf_alloc<<<cblocks(nl), kCB, 0, s>>>(leaf.v, first, nl, sbits, bbits, B.runs, rscan, B.bits, wscan, p->color_leaves, p->color_ctr,
@@ -1136,9 +1277,9 @@ hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, 
 			HD_LAUNCH_CHECK();
 			k_flags<<<cblocks(n), kCB, 0, s>>>(colors, bw, n, sbits, flag, bits);
 			HD_LAUNCH_CHECK();
-			st = exclusive_scan(p, flag, fscan, n);
+			st = exclusive_scan(p, flag, fscan, n, s);
 			if (st == HD_OK)
-				st = exclusive_scan(p, bits, bscan, n);
+				st = exclusive_scan(p, bits, bscan, n, s);
 			if (st == HD_OK) { // how many words will this batch append?  grow the leaf array once, before allocating
 				unsigned long long *total = nullptr, need = 0;
 				HD_CUDA_TRY(cmalloc(&total, 1, s));
@@ -1148,7 +1289,9 @@ hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, 
 				HD_CUDA_TRY(cudaMemcpyAsync(&need, total, 8, cudaMemcpyDeviceToHost, s));
 				HD_CUDA_TRY(cudaStreamSynchronize(s));
 				cudaFreeAsync(total, s);
-				st = ensure_color_storage(p, p->color_node_words, p->color_leaf_words + need);
+				st = finish_geometry();
+				if (st == HD_OK)
+					st = ensure_color_storage(p, p->color_node_words, p->color_leaf_words + need);
 			}
 			if (st == HD_OK) {
 				k_leaf_alloc<<<cblocks(nl), kCB, 0, s>>>(leaf.v, first, nl, sbits, sbits, flag, fscan, bits, bscan, p->color_leaves, p->color_ctr,
@@ -1178,6 +1321,11 @@ hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, 
 	}
 
 	// ---- octree nodes bottom-up (SetNode) ----
+	st = finish_geometry(); // edits that touch no colour leaf get here with the rebuild still in flight
+	if (st != HD_OK) {
+		cleanup();
+		return st;
+	}
 	{
 		uint64_t new_nodes = 0;
 		for (uint32_t l = 0; l <= deepest && l < LL; ++l)
@@ -1188,13 +1336,23 @@ hd_status hd_edit_color(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit, 
 			return st;
 		}
 	}
-	for (uint32_t l = std::min(deepest, LL ? LL - 1 : 0) + 1; l-- > 0;) {
-		if (l >= LL || inner[l].v.n == 0)
-			continue;
-		k_cup<<<cblocks(inner[l].v.n), kCB, 0, s>>>(inner[l].v, p->color_nodes, p->color_ctr, p->color_node_cap,
-		                                          l ? inner[l - 1].v.child : nullptr, root_dev);
-		HD_LAUNCH_CHECK();
-	}
+	if (sized) { // brush-sized edit: all levels in one launch
+		CLevels all{};
+		const uint32_t top = std::min(std::min(deepest, LL ? LL - 1 : 0) + 1, LL);
+		for (uint32_t l = 0; l < top; ++l)
+			all.lv[l] = inner[l].v;
+		if (top) {
+			k_cup_all<<<1, kOctThreads, 0, s>>>(all, top, p->color_nodes, p->color_ctr, p->color_node_cap, root_dev);
+			HD_LAUNCH_CHECK();
+		}
+	} else
+		for (uint32_t l = std::min(deepest, LL ? LL - 1 : 0) + 1; l-- > 0;) {
+			if (l >= LL || inner[l].v.n == 0)
+				continue;
+			k_cup<<<cblocks(inner[l].v.n), kCB, 0, s>>>(inner[l].v, p->color_nodes, p->color_ctr, p->color_node_cap,
+			                                          l ? inner[l - 1].v.child : nullptr, root_dev);
+			HD_LAUNCH_CHECK();
+		}
 	uint32_t ctr[4], new_color_root;
 	HD_CUDA_TRY(cudaMemcpyAsync(ctr, p->color_ctr, sizeof(ctr), cudaMemcpyDeviceToHost, s));
 	HD_CUDA_TRY(cudaMemcpyAsync(&new_color_root, root_dev, 4, cudaMemcpyDeviceToHost, s));

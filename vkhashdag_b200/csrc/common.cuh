@@ -102,6 +102,7 @@ struct hd_pool {
 	uint64_t color_node_cap = 0, color_leaf_cap = 0;     // allocated words
 	uint32_t color_root = HD_COLOR_NULL, color_leaf_level = 0;
 	uint32_t *color_ctr = nullptr; // device: [0] = nodes used, [1] = leaf words used, [2] = out-of-space flag
+	cudaStream_t color_stream = nullptr; // hd_edit_color runs its octree pass here while the geometry rebuild is in flight
 	// colour replica sync (sync.cu): nodes and appended leaf chunks are append-only, chunks rewritten in place since the
 	// last sync are listed on the device (color.cu appends to the list)
 	uint64_t color_synced_node_words = 0, color_synced_leaf_words = 0;
@@ -153,12 +154,16 @@ struct hd_pool {
 
 namespace hd {
 hd_status edit_scratch_free(hd_pool *pool);
+// the one-launch rebuild in two halves (edit.cu): prepare, enqueue without waiting, wait + report
+hd_status edit_prepare(hd_pool *pool);
+hd_status fast_edit_begin(hd_pool *pool, uint32_t root_in, const hd_edit_desc *edits, uint32_t n, bool *launched, bool share_gpu);
+hd_status fast_edit_end(hd_pool *pool, uint32_t *root_out, hd_edit_stats *stats, bool *handled);
 hd_status ensure_filled(hd_pool *pool);
 hd_status upsert_batch_dev(hd_pool *pool, uint32_t level, uint32_t n, uint32_t stride, const uint32_t *cand_dev,
                            uint32_t *result_dev);
 hd_status set_filled(hd_pool *pool, const std::vector<uint32_t> &filled);
 // device-wide exclusive prefix sum over u32 (color.cu); in == out is allowed
-hd_status exclusive_scan(hd_pool *pool, const uint32_t *in, uint32_t *out, uint64_t n);
+hd_status exclusive_scan(hd_pool *pool, const uint32_t *in, uint32_t *out, uint64_t n, cudaStream_t stream = nullptr);
 constexpr uint32_t kColorDirtyCap = 1u << 20; // entries of hd_pool::color_dirty_list
 hd_status ensure_color_storage(hd_pool *p, uint64_t node_words, uint64_t leaf_words); // color.cu
 } // namespace hd

@@ -119,6 +119,7 @@ struct FastPath {
 	FastDyn *dyn_host_dev = nullptr; // device-side addresses of the mapped host blocks
 	DevCounters *ctr_host_dev = nullptr;
 	uint32_t fused_grid = 0;
+	uint32_t pending_edits = 0; // editors of the call in flight between fast_edit_begin and fast_edit_end
 };
 
 struct EditScratch {
@@ -1308,6 +1309,8 @@ __device__ __forceinline__ uint32_t warp_find(const uint32_t *words, uint32_t ba
 	const uint32_t lane = threadIdx.x & 31u, full = 0xFFFFFFFFu;
 	const uint32_t c0 = me[0], c1 = me[1];
 	uint32_t found = kNull;
+	// (512 words per trip instead of 128 was tried: 0.93 -> 1.04 ms on a 100-editor batch.  The deep levels' scans are bound by
+	// the volume read through L2 — 83 000 items x 1 200 words at level 14 of the cfg3 scene —, not by the trips' latency.)
 	if (is_leaf) {
 		for (uint32_t off = from & ~1u; off < to && found == kNull; off += 128u) {
 			uint2 w[2];
@@ -2467,10 +2470,15 @@ static hd_status fast_build(hd_pool *p) {
 	return HD_OK;
 }
 
-// Returns HD_OK with *handled = true when the call was served here; *handled = false sends it to the general path.
-static hd_status fast_edit(hd_pool *p, uint32_t root_in, const hd_edit_desc *edits, uint32_t n, uint32_t *root_out,
-                           hd_edit_stats *stats, bool *handled) {
-	*handled = false;
+// The one-launch rebuild in two halves, so that a caller can run other work while the kernel is in flight (the colour edit
+// overlaps its octree pass, color.cu).  fast_edit_begin enqueues the rebuild on the pool's stream when the batch qualifies
+// (*launched = true) and returns without waiting; fast_edit_end waits for it and reports: *handled = true when the call
+// was served, false when a work queue turned out too small — nothing was written to the pool then and the general path
+// must redo the call.
+// share_gpu: launch one CTA per SM instead of two — two 512-thread CTAs of 64 registers take an SM's whole register file,
+// and nothing the caller enqueues on another stream could run beside the rebuild.
+hd_status fast_edit_begin(hd_pool *p, uint32_t root_in, const hd_edit_desc *edits, uint32_t n, bool *launched, bool share_gpu) {
+	*launched = false;
 	static const bool enabled = !(getenv("HD_EDIT_FAST") && atoi(getenv("HD_EDIT_FAST")) == 0); // 0 general, 1 fused, 2 graph
 	EditScratch *s = p->edit;
 	FastPath &f = s->fast;
@@ -2503,13 +2511,23 @@ static hd_status fast_edit(hd_pool *p, uint32_t root_in, const hd_edit_desc *edi
 			a.lv[l] = f.lv[l];
 		a.fast_scan = s->fast_scan;
 		void *params[] = {&a};
-		HD_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_edit_fused, dim3(f.fused_grid), dim3(kFusedThreads), params, 0,
-		                                        p->stream));
+		const uint32_t grid = share_gpu ? std::min<uint32_t>(f.fused_grid, uint32_t(p->sm_count > 0 ? p->sm_count : 148)) : f.fused_grid;
+		HD_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_edit_fused, dim3(grid), dim3(kFusedThreads), params, 0, p->stream));
 		g_launches.fetch_add(1, std::memory_order_relaxed);
 	} else {
 		HD_CUDA_TRY(cudaGraphLaunch(f.exec, p->stream));
 		g_launches.fetch_add(f.kernels, std::memory_order_relaxed);
 	}
+	f.pending_edits = n;
+	*launched = true;
+	return HD_OK;
+}
+
+hd_status fast_edit_end(hd_pool *p, uint32_t *root_out, hd_edit_stats *stats, bool *handled) {
+	*handled = false;
+	EditScratch *s = p->edit;
+	FastPath &f = s->fast;
+	const uint32_t L = p->geo.node_levels, n = f.pending_edits;
 	HD_CUDA_TRY(cudaStreamSynchronize(p->stream));
 	const DevCounters &c = *f.ctr_host;
 	if (c.error)
@@ -2538,6 +2556,27 @@ static hd_status fast_edit(hd_pool *p, uint32_t root_in, const hd_edit_desc *edi
 	return HD_OK;
 }
 
+// the scratch both halves and the general path need (hd_edit_batch's preamble)
+hd_status edit_prepare(hd_pool *p) {
+	hd_status st = scratch_init(p);
+	if (st == HD_OK)
+		st = ensure_filled(p); // NodePool.hpp:408
+	if (st == HD_OK)
+		p->edit->last_path = 0;
+	return st;
+}
+
+// Returns HD_OK with *handled = true when the call was served here; *handled = false sends it to the general path.
+static hd_status fast_edit(hd_pool *p, uint32_t root_in, const hd_edit_desc *edits, uint32_t n, uint32_t *root_out,
+                           hd_edit_stats *stats, bool *handled) {
+	*handled = false;
+	bool launched = false;
+	hd_status st = fast_edit_begin(p, root_in, edits, n, &launched, false);
+	if (st != HD_OK || !launched)
+		return st;
+	return fast_edit_end(p, root_out, stats, handled);
+}
+
 } // namespace hd
 
 using namespace hd;
@@ -2559,13 +2598,10 @@ hd_status hd_edit_batch(hd_pool *p, uint32_t root_in, const hd_edit_desc *edits,
 			return HD_ERR_INVALID;
 		}
 	HD_CUDA_TRY(cudaSetDevice(p->device));
-	hd_status st = scratch_init(p);
-	if (st == HD_OK)
-		st = ensure_filled(p); // NodePool.hpp:408
+	hd_status st = edit_prepare(p);
 	if (st != HD_OK)
 		return st;
 	bool handled = false;
-	p->edit->last_path = 0;
 	st = fast_edit(p, root_in, edits, n, root_out, stats, &handled);
 	if (st != HD_OK || handled) {
 		if (st != HD_OK)

@@ -229,6 +229,8 @@ void hd_pool_destroy(hd_pool *p) {
 	}
 	if (p->copy_stream)
 		cudaStreamDestroy(p->copy_stream);
+	if (p->color_stream)
+		cudaStreamDestroy(p->color_stream);
 	if (p->stream)
 		cudaStreamDestroy(p->stream);
 	delete p;
