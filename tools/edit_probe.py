@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--mid", type=int, default=0, help="also time batches of this many editors (mid-size batches)")
     ap.add_argument("--l14", type=int, default=0, help="override the bucket bits of node level 14")
+    ap.add_argument("--color", type=int, default=0, help="also time this many coloured r=128 brushes like bench.py's color_brush leg")
     a = ap.parse_args()
     if a.l14:
         bench.CFG3_BUCKET_BITS[14] = a.l14
@@ -66,6 +67,28 @@ def main():
             rb = pool.EditBatch(rb, sub)
             ms.append((time.perf_counter() - t0) * 1e3)
         out["mid"] = {"editors": a.mid, "ms_median": round(float(np.median(ms[2:])), 4), "path": pool.last_stats["path"]}
+    if a.color:
+        pool.SetRoot(root_b)
+        pool.ColorConfig(bench.COLOR_LEAF_LEVEL)
+        res3 = 1 << vl
+        pool.EditColor(root_b, abi.sphere((res3 // 2,) * 3, 3 * res3 * res3), 0x60C0E0, paint=True)   # base coat
+        scale = (1 << bench.CFG3_PATCH_BITS) / float(res3)
+        g = pool.Trace(bench.camera(cfg, root_b, 5, 96, 54, False, scale=scale), want=("hits",))["hits"].reshape(-1)
+        g = g[(g["packed"] >> 31) != 0]
+        picks = g[np.linspace(0, len(g) - 1, a.color).astype(int)]
+        palette = [0xE04020, 0x20A040, 0x3060E0, 0xE0C020, 0xA040C0]
+        broot, ms, kinds = root_b, [], []
+        torch.cuda.profiler.start()
+        for i, h in enumerate(picks):
+            d = abi.sphere(tuple(int(c) for c in h["vox"]), 128 * 128)
+            t0 = time.perf_counter()
+            broot, _ = pool.EditColor(broot, d, palette[i % 5], i % 3 == 2)
+            ms.append(round((time.perf_counter() - t0) * 1e3, 4))
+            kinds.append("paint" if i % 3 == 2 else "fill")
+        torch.cuda.profiler.stop()
+        out["color"] = {"ms": ms, "kinds": kinds, "median_fill": float(np.median([m for m, k in zip(ms, kinds) if k == "fill"][2:])),
+                        "median_paint": float(np.median([m for m, k in zip(ms, kinds) if k == "paint"][1:])),
+                        "median_all": float(np.median(ms[4:]))}
     print(json.dumps(out))
     pool.close()
 

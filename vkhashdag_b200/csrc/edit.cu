@@ -664,8 +664,9 @@ __device__ __forceinline__ void phase_down(const Geometry &g, uint32_t level /* 
                                            const uint32_t *__restrict__ words, const hd_edit_desc *__restrict__ edits,
                                            const uint32_t *__restrict__ filled, const LevelView &in, const LevelView &out,
                                            DevCounters *ctr, uint32_t *items_ctr, uint32_t *entries_ctr, uint32_t tid0,
-                                           uint32_t nthreads, uint32_t *s_alloc) {
-	const uint32_t n8 = in.count() * 8u;
+                                           uint32_t nthreads, uint32_t *s_alloc, uint32_t n_known = 0xFFFFFFFFu) {
+	// n_known: the caller already holds the level's item count (the solo stage of the fused kernel keeps it in shared memory)
+	const uint32_t n8 = (n_known != 0xFFFFFFFFu ? n_known : in.count()) * 8u;
 	const uint32_t bits = g.voxel_level() - (level + 1u);
 	const bool serial_long = !kWarpAlloc && in.n_dev != nullptr;
 	// whole CTAs (alloc_item synchronises) or whole warps (alloc_item_warp shuffles) iterate together
@@ -1303,14 +1304,17 @@ __global__ void __launch_bounds__(kBlock) k_upsert(Geometry g, uint32_t level, b
 // find over [0, bucket_words), take the bucket's lock, re-find over what was appended meanwhile, append, publish
 // bucket_words, unlock.  Scans read through L2 (__ldcg: another SM's append is never hidden by a stale L1 line) and a
 // writer fences before it publishes bucket_words, so every word below a bucket_words value a scanner read is complete.
+// (Two variations of this scan were measured and dropped.  512 words per trip instead of 128: the deep levels of a mid-size batch
+// are bound by the volume read through L2 — 83 000 items x 1 200 words at level 14 of the cfg3 scene —, and loading past a hit adds
+// to it: 100-editor batch 0.93 -> 1.04 ms.  Verifying header matches one candidate at a time with the whole warp instead of every
+// lane verifying its own: the header is just the 8-bit child mask, dozens of nodes of a bucket share it, and the verifications
+// become a chain of dependent round trips: level 14 of the same batch 263 -> 402 us.)
 __device__ __forceinline__ uint32_t warp_find(const uint32_t *words, uint32_t base, uint32_t from, uint32_t to,
                                               const uint32_t *me /* shared */, uint32_t nw, bool is_leaf, bool fast_scan,
                                               uint32_t wpp) {
 	const uint32_t lane = threadIdx.x & 31u, full = 0xFFFFFFFFu;
 	const uint32_t c0 = me[0], c1 = me[1];
 	uint32_t found = kNull;
-	// (512 words per trip instead of 128 was tried: 0.93 -> 1.04 ms on a 100-editor batch.  The deep levels' scans are bound by
-	// the volume read through L2 — 83 000 items x 1 200 words at level 14 of the cfg3 scene —, not by the trips' latency.)
 	if (is_leaf) {
 		for (uint32_t off = from & ~1u; off < to && found == kNull; off += 128u) {
 			uint2 w[2];
@@ -1384,7 +1388,7 @@ struct UpStats {
 };
 __device__ __forceinline__ uint32_t warp_upsert(const Geometry &g, uint32_t level, bool fast_scan, const uint32_t *me,
                                                 uint32_t nw, uint32_t fallback, uint32_t *words, uint32_t *bucket_words,
-                                                uint32_t *locks, UpStats &st) {
+                                                uint32_t *locks, UpStats &st, uint32_t lock_mask = 0xFFFFFFFFu) {
 	const uint32_t lane = threadIdx.x & 31u, full = 0xFFFFFFFFu;
 	const bool is_leaf = level == g.node_levels - 1u;
 	const uint32_t wpp = g.words_per_page(), wpb = g.words_per_bucket();
@@ -1398,7 +1402,7 @@ __device__ __forceinline__ uint32_t warp_upsert(const Geometry &g, uint32_t leve
 	if (found != kNull)
 		return found;
 	if (lane == 0) {
-		while (atomicCAS(locks + bucket, 0u, 1u) != 0u)
+		while (atomicCAS(locks + (bucket & lock_mask), 0u, 1u) != 0u)
 			__nanosleep(32);
 		__threadfence();
 	}
@@ -1428,7 +1432,7 @@ __device__ __forceinline__ uint32_t warp_upsert(const Geometry &g, uint32_t leve
 	__syncwarp(full);
 	if (lane == 0) {
 		__threadfence();
-		atomicExch(locks + bucket, 0u);
+		atomicExch(locks + (bucket & lock_mask), 0u);
 	}
 	return found;
 }
@@ -1438,7 +1442,10 @@ __device__ __forceinline__ uint32_t warp_upsert(const Geometry &g, uint32_t leve
 __device__ __forceinline__ void phase_up(const Geometry &g, uint32_t level, bool fast_scan, uint32_t *words,
                                          uint32_t *bucket_words, uint32_t *locks, const hd_edit_desc *__restrict__ edits,
                                          const LevelView &lv, uint32_t *parent_child_new, DevCounters *ctr,
-                                         uint32_t (*s_cand)[12], uint32_t tid0, uint32_t nthreads) {
+                                         uint32_t (*s_cand)[12], uint32_t tid0, uint32_t nthreads,
+                                         uint32_t lock_mask = 0xFFFFFFFFu) {
+	// lock_mask: `locks` holds one word per bucket (all ones), or — when one CTA finishes the small levels alone and nobody
+	// else touches the pool — a few words of shared memory indexed by the bucket's low bits (no global atomics)
 	const uint32_t lane = threadIdx.x & 31u, full = 0xFFFFFFFFu, n = lv.count();
 	const uint32_t warps = nthreads >> 5;
 	const bool is_leaf = level == g.node_levels - 1u;
@@ -1502,7 +1509,7 @@ __device__ __forceinline__ void phase_up(const Geometry &g, uint32_t level, bool
 		}
 		if (insert) {
 			__syncwarp(full);
-			res = warp_upsert(g, level, fast_scan, me, nw, cur, words, bucket_words, locks, st);
+			res = warp_upsert(g, level, fast_scan, me, nw, cur, words, bucket_words, locks, st, lock_mask);
 			__syncwarp(full);
 		}
 		if (lane == 0) {
@@ -1554,6 +1561,10 @@ __global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_const
 	__shared__ uint32_t s_cand[kFusedThreads / 32][12];
 	__shared__ uint32_t s_alloc[2 * (kMaxWarps + 1)];
 	__shared__ uint32_t s_first_big;
+	// the levels CTA 0 walks alone keep what every trip needs on chip: the queue counters of the level being produced, the
+	// editors' descriptors and the bucket locks (each of them was a dependent L2 round trip per level)
+	__shared__ uint32_t s_ctr[2], s_locks[64];
+	__shared__ hd_edit_desc s_edits[32];
 	cg::grid_group grid = cg::this_grid();
 	const Geometry &g = a.g;
 	const uint32_t L = g.node_levels;
@@ -1567,23 +1578,45 @@ __global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_const
 		for (uint32_t i = threadIdx.x; i < sizeof(DevCounters) / 4; i += blockDim.x)
 			reinterpret_cast<uint32_t *>(ctr)[i] = 0u;
 		// only the header and the descriptors in use cross PCIe (a brush call is 56 bytes, not the 40 KB the struct can hold)
-		const uint32_t n_words = 4u + min(reinterpret_cast<const volatile uint32_t *>(a.dyn_host)[1], kFastMaxEdits) *
-		                                  uint32_t(sizeof(hd_edit_desc) / 4);
-		for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x)
-			reinterpret_cast<uint32_t *>(a.dyn_dev)[i] = reinterpret_cast<const volatile uint32_t *>(a.dyn_host)[i];
+		const uint32_t n_edits = min(reinterpret_cast<const volatile uint32_t *>(a.dyn_host)[1], kFastMaxEdits);
+		const uint32_t n_words = 4u + n_edits * uint32_t(sizeof(hd_edit_desc) / 4);
+		for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) { // up to 32 editors also stay in shared memory
+			const uint32_t w = reinterpret_cast<const volatile uint32_t *>(a.dyn_host)[i];
+			reinterpret_cast<uint32_t *>(a.dyn_dev)[i] = w;
+			if (i >= 4u && n_edits <= 32u)
+				reinterpret_cast<uint32_t *>(s_edits)[i - 4u] = w;
+		}
+		if (threadIdx.x < 64)
+			s_locks[threadIdx.x] = 0u;
 		__syncthreads();
+		const hd_edit_desc *edits_solo = n_edits <= 32u ? s_edits : edits;
 		if (threadIdx.x == 0)
 			phase_stamp(ctr);
 		if (threadIdx.x < 32)
-			phase_root(g, edits, a.dyn_dev->n_edits, a.iota, a.filled, a.dyn_dev->root, a.lv[0], ctr);
+			phase_root(g, edits_solo, a.dyn_dev->n_edits, a.iota, a.filled, a.dyn_dev->root, a.lv[0], ctr);
 		__syncthreads();
-		uint32_t l = 0;
-		// (levels whose lists are longer than 32 entries go to the grid: a warp per (item, child) pair)
-		for (; l + 1 < L && items[l] <= kSoloDown && *(volatile uint32_t *)&ctr->lvl_long[l] == 0u; ++l) {
-			phase_down<false, true>(g, l, a.words, edits, a.filled, a.lv[l], a.lv[l + 1], ctr, &ctr->lvl_items[l + 1],
-			                        &ctr->lvl_entries[l + 1], threadIdx.x, blockDim.x, s_alloc);
-			__syncthreads();
-		}
+		uint32_t l = 0, n_cur = items[0];
+		// (levels whose lists are longer than 32 entries go to the grid: a warp per (item, child) pair; only the root's
+		// flag can be set here, phase_down_long is what sets the others)
+		if (*(volatile uint32_t *)&ctr->lvl_long[0] == 0u)
+			for (; l + 1 < L && n_cur != 0u && n_cur <= kSoloDown; ++l) {
+				if (threadIdx.x == 0)
+					s_ctr[0] = 0u, s_ctr[1] = 0u;
+				__syncthreads();
+				phase_down<false, true>(g, l, a.words, edits_solo, a.filled, a.lv[l], a.lv[l + 1], ctr, &s_ctr[0], &s_ctr[1],
+				                        threadIdx.x, blockDim.x, s_alloc, n_cur);
+				__syncthreads();
+				const uint32_t n_next = s_ctr[0], e_next = s_ctr[1];
+				if (threadIdx.x == 0)
+					ctr->lvl_items[l + 1] = n_next, ctr->lvl_entries[l + 1] = e_next;
+				__syncthreads(); // s_ctr is reset by the next trip
+				n_cur = n_next;
+				if (n_next > a.lv[l + 1].cap || e_next > a.lv[l + 1].cap_entries) { // queue overflow: DevCounters::error is set
+					++l;
+					break;
+				}
+			}
+		__threadfence(); // the grid reads the queues and counts written above
 		if (threadIdx.x == 0)
 			ctr->next_items = l, phase_stamp(ctr); // first level the whole grid expands
 	}
@@ -1617,10 +1650,15 @@ __global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_const
 	}
 	if (blockIdx.x != 0)
 		return;
-	for (uint32_t l = solo; l-- > 0;) {
-		phase_up(g, l, a.fast_scan, a.words, a.bucket_words, a.locks, edits, a.lv[l], l ? a.lv[l - 1].child_new : nullptr, ctr, s_cand,
-		         threadIdx.x, blockDim.x);
-		__syncthreads();
+	{
+		// every other CTA has left (or waits in nothing: there is no grid barrier below): shared-memory locks and descriptors
+		const uint32_t n_edits = min(a.dyn_dev->n_edits, kFastMaxEdits);
+		const hd_edit_desc *edits_solo = n_edits <= 32u ? s_edits : edits;
+		for (uint32_t l = solo; l-- > 0;) {
+			phase_up(g, l, a.fast_scan, a.words, a.bucket_words, s_locks, edits_solo, a.lv[l], l ? a.lv[l - 1].child_new : nullptr, ctr,
+			         s_cand, threadIdx.x, blockDim.x, 63u);
+			__syncthreads();
+		}
 	}
 	if (threadIdx.x == 0)
 		phase_stamp(ctr);
