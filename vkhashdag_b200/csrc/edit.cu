@@ -1304,42 +1304,43 @@ __global__ void __launch_bounds__(kBlock) k_upsert(Geometry g, uint32_t level, b
 // find over [0, bucket_words), take the bucket's lock, re-find over what was appended meanwhile, append, publish
 // bucket_words, unlock.  Scans read through L2 (__ldcg: another SM's append is never hidden by a stale L1 line) and a
 // writer fences before it publishes bucket_words, so every word below a bucket_words value a scanner read is complete.
-// (Two variations of this scan were measured and dropped.  512 words per trip instead of 128: the deep levels of a mid-size batch
-// are bound by the volume read through L2 — 83 000 items x 1 200 words at level 14 of the cfg3 scene —, and loading past a hit adds
-// to it: 100-editor batch 0.93 -> 1.04 ms.  Verifying header matches one candidate at a time with the whole warp instead of every
-// lane verifying its own: the header is just the 8-bit child mask, dozens of nodes of a bucket share it, and the verifications
-// become a chain of dependent round trips: level 14 of the same batch 263 -> 402 us.)
-__device__ __forceinline__ uint32_t warp_find(const uint32_t *words, uint32_t base, uint32_t from, uint32_t to,
-                                              const uint32_t *me /* shared */, uint32_t nw, bool is_leaf, bool fast_scan,
-                                              uint32_t wpp) {
+// kLoads = 4-byte loads per lane and trip.  Measured on the one-launch kernel: 16 (512 words per trip) instead of 4 takes 5 % off
+// a 100-editor batch (level 14 of the cfg3 scene, 83 000 items x 1 200 words: 256 -> 220 us) and nothing off a single brush.
+// Dropped: verifying header matches one candidate at a time with the whole warp instead of every lane verifying its own —
+// the header is just the 8-bit child mask, dozens of nodes of a bucket share it, and the verifications become a chain of
+// dependent round trips (the same level 263 -> 402 us).
+template <int kLoads>
+__device__ __forceinline__ uint32_t warp_find_t(const uint32_t *words, uint32_t base, uint32_t from, uint32_t to,
+                                                const uint32_t *me /* shared */, uint32_t nw, bool is_leaf, bool fast_scan,
+                                                uint32_t wpp) {
 	const uint32_t lane = threadIdx.x & 31u, full = 0xFFFFFFFFu;
 	const uint32_t c0 = me[0], c1 = me[1];
 	uint32_t found = kNull;
 	if (is_leaf) {
-		for (uint32_t off = from & ~1u; off < to && found == kNull; off += 128u) {
-			uint2 w[2];
+		for (uint32_t off = from & ~1u; off < to && found == kNull; off += kLoads * 32u) {
+			uint2 w[kLoads / 2];
 #pragma unroll
-			for (int k = 0; k < 2; ++k) {
+			for (int k = 0; k < kLoads / 2; ++k) {
 				const uint32_t q = off + k * 64u + lane * 2u;
 				w[k] = q + 2u <= to ? __ldcg(reinterpret_cast<const uint2 *>(words + base + q)) : make_uint2(0u, 0u);
 			}
 #pragma unroll
-			for (int k = 0; k < 2; ++k) {
+			for (int k = 0; k < kLoads / 2; ++k) {
 				const uint32_t m = __ballot_sync(full, w[k].x == c0 && w[k].y == c1);
 				if (m && found == kNull)
 					found = base + off + k * 64u + (__ffs(m) - 1u) * 2u;
 			}
 		}
 	} else if (fast_scan) {
-		for (uint32_t off = from; off < to && found == kNull; off += 128u) {
-			uint32_t w[4];
+		for (uint32_t off = from; off < to && found == kNull; off += kLoads * 32u) {
+			uint32_t w[kLoads];
 #pragma unroll
-			for (int k = 0; k < 4; ++k) {
+			for (int k = 0; k < kLoads; ++k) {
 				const uint32_t q = off + k * 32u + lane;
 				w[k] = q + nw <= to ? __ldcg(words + base + q) : 0u;
 			}
 #pragma unroll
-			for (int k = 0; k < 4; ++k) {
+			for (int k = 0; k < kLoads; ++k) {
 				const uint32_t q = off + k * 32u + lane;
 				bool hit = w[k] == c0; // c0 != 0: out-of-range slots (0) never match
 				if (hit) { // header match (rare unless it is the node): all child words in flight at once, then compare
@@ -1382,13 +1383,20 @@ __device__ __forceinline__ uint32_t warp_find(const uint32_t *words, uint32_t ba
 	return found;
 }
 
+// 512 words per trip in the one-launch kernel (FusedArgs::wide_scan; 5 % on a 100-editor batch), 128 elsewhere
+__device__ __forceinline__ uint32_t warp_find(const uint32_t *words, uint32_t base, uint32_t from, uint32_t to,
+                                              const uint32_t *me /* shared */, uint32_t nw, bool is_leaf, bool fast_scan,
+                                              uint32_t wpp, bool wide = false) {
+	return wide && to - from > 128u ? warp_find_t<16>(words, base, from, to, me, nw, is_leaf, fast_scan, wpp)
+	                                : warp_find_t<4>(words, base, from, to, me, nw, is_leaf, fast_scan, wpp);
+}
 struct UpStats {
 	uint32_t upserts, nodes, words, overflow;
 	unsigned long long scan;
 };
 __device__ __forceinline__ uint32_t warp_upsert(const Geometry &g, uint32_t level, bool fast_scan, const uint32_t *me,
                                                 uint32_t nw, uint32_t fallback, uint32_t *words, uint32_t *bucket_words,
-                                                uint32_t *locks, UpStats &st, uint32_t lock_mask = 0xFFFFFFFFu) {
+                                                uint32_t *locks, UpStats &st, uint32_t lock_mask = 0xFFFFFFFFu, bool wide = false) {
 	const uint32_t lane = threadIdx.x & 31u, full = 0xFFFFFFFFu;
 	const bool is_leaf = level == g.node_levels - 1u;
 	const uint32_t wpp = g.words_per_page(), wpb = g.words_per_bucket();
@@ -1397,7 +1405,7 @@ __device__ __forceinline__ uint32_t warp_upsert(const Geometry &g, uint32_t leve
 	const uint32_t base = bucket << g.bucket_shift();
 	volatile uint32_t *bwp = bucket_words + bucket;
 	const uint32_t bw = *bwp;
-	uint32_t found = warp_find(words, base, 0u, bw, me, nw, is_leaf, fast_scan, wpp);
+	uint32_t found = warp_find(words, base, 0u, bw, me, nw, is_leaf, fast_scan, wpp, wide);
 	st.upserts += 1, st.scan += bw;
 	if (found != kNull)
 		return found;
@@ -1409,7 +1417,7 @@ __device__ __forceinline__ uint32_t warp_upsert(const Geometry &g, uint32_t leve
 	__syncwarp(full);
 	const uint32_t bw2 = *bwp;
 	if (bw2 > bw) { // somebody appended between the scan and the lock: look at the new tail only (NodePool.hpp:187-192)
-		found = warp_find(words, base, bw, bw2, me, nw, is_leaf, fast_scan, wpp);
+		found = warp_find(words, base, bw, bw2, me, nw, is_leaf, fast_scan, wpp, wide);
 		st.scan += bw2 - bw;
 	}
 	if (found == kNull) {
@@ -1443,7 +1451,7 @@ __device__ __forceinline__ void phase_up(const Geometry &g, uint32_t level, bool
                                          uint32_t *bucket_words, uint32_t *locks, const hd_edit_desc *__restrict__ edits,
                                          const LevelView &lv, uint32_t *parent_child_new, DevCounters *ctr,
                                          uint32_t (*s_cand)[12], uint32_t tid0, uint32_t nthreads,
-                                         uint32_t lock_mask = 0xFFFFFFFFu) {
+                                         uint32_t lock_mask = 0xFFFFFFFFu, bool wide = false) {
 	// lock_mask: `locks` holds one word per bucket (all ones), or — when one CTA finishes the small levels alone and nobody
 	// else touches the pool — a few words of shared memory indexed by the bucket's low bits (no global atomics)
 	const uint32_t lane = threadIdx.x & 31u, full = 0xFFFFFFFFu, n = lv.count();
@@ -1509,7 +1517,7 @@ __device__ __forceinline__ void phase_up(const Geometry &g, uint32_t level, bool
 		}
 		if (insert) {
 			__syncwarp(full);
-			res = warp_upsert(g, level, fast_scan, me, nw, cur, words, bucket_words, locks, st, lock_mask);
+			res = warp_upsert(g, level, fast_scan, me, nw, cur, words, bucket_words, locks, st, lock_mask, wide);
 			__syncwarp(full);
 		}
 		if (lane == 0) {
@@ -1556,6 +1564,7 @@ struct FusedArgs {
 	DevCounters *ctr, *ctr_host; // ctr_host: mapped pinned host memory
 	LevelView lv[HD_MAX_NODE_LEVELS];
 	bool fast_scan;
+	bool wide_scan; // 512-word scan trips in the bottom-up phases (default; HD_EDIT_SCAN_WIDE=0: 128 words, for A/B runs)
 };
 __global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_constant__ FusedArgs a) {
 	__shared__ uint32_t s_cand[kFusedThreads / 32][12];
@@ -1643,7 +1652,7 @@ __global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_const
 	const uint32_t solo = s_first_big;
 	for (uint32_t l = L; l-- > solo;) {
 		phase_up(g, l, a.fast_scan, a.words, a.bucket_words, a.locks, edits, a.lv[l], l ? a.lv[l - 1].child_new : nullptr, ctr, s_cand,
-		         gtid, gthreads);
+		         gtid, gthreads, 0xFFFFFFFFu, a.wide_scan);
 		grid.sync();
 		if (gtid == 0)
 			phase_stamp(ctr);
@@ -1656,7 +1665,7 @@ __global__ void __launch_bounds__(kFusedThreads) k_edit_fused(const __grid_const
 		const hd_edit_desc *edits_solo = n_edits <= 32u ? s_edits : edits;
 		for (uint32_t l = solo; l-- > 0;) {
 			phase_up(g, l, a.fast_scan, a.words, a.bucket_words, s_locks, edits_solo, a.lv[l], l ? a.lv[l - 1].child_new : nullptr, ctr,
-			         s_cand, threadIdx.x, blockDim.x, 63u);
+			         s_cand, threadIdx.x, blockDim.x, 63u, a.wide_scan);
 			__syncthreads();
 		}
 	}
@@ -2548,6 +2557,8 @@ hd_status fast_edit_begin(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit
 		for (uint32_t l = 0; l < L; ++l)
 			a.lv[l] = f.lv[l];
 		a.fast_scan = s->fast_scan;
+		static const bool wide_scan = !(getenv("HD_EDIT_SCAN_WIDE") && atoi(getenv("HD_EDIT_SCAN_WIDE")) == 0);
+		a.wide_scan = wide_scan;
 		void *params[] = {&a};
 		const uint32_t grid = share_gpu ? std::min<uint32_t>(f.fused_grid, uint32_t(p->sm_count > 0 ? p->sm_count : 148)) : f.fused_grid;
 		HD_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_edit_fused, dim3(grid), dim3(kFusedThreads), params, 0, p->stream));
