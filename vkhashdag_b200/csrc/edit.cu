@@ -2560,7 +2560,13 @@ hd_status fast_edit_begin(hd_pool *p, uint32_t root_in, const hd_edit_desc *edit
 		static const bool wide_scan = !(getenv("HD_EDIT_SCAN_WIDE") && atoi(getenv("HD_EDIT_SCAN_WIDE")) == 0);
 		a.wide_scan = wide_scan;
 		void *params[] = {&a};
-		const uint32_t grid = share_gpu ? std::min<uint32_t>(f.fused_grid, uint32_t(p->sm_count > 0 ? p->sm_count : 148)) : f.fused_grid;
+		// One CTA per SM for a brush-sized call (a handful of editors): the grid barriers are cheaper with half the CTAs, and a
+		// single r <= 128 brush has no level that needs more than 148 x 16 warps (measured, r = 2 / 32 / 128 / 256: 0.173 / 0.201 /
+		// 0.229 / 0.274 ms with two CTAs per SM, 0.162 / 0.184 / 0.216 / 0.283 with one; 100 editors need both).
+		uint32_t grid = share_gpu || n <= 4u ? std::min<uint32_t>(f.fused_grid, uint32_t(p->sm_count > 0 ? p->sm_count : 148)) : f.fused_grid;
+		static const uint32_t forced_grid = getenv("HD_EDIT_FUSED_GRID") ? uint32_t(atoi(getenv("HD_EDIT_FUSED_GRID"))) : 0u;
+		if (forced_grid) // A/B knob: fewer CTAs make the grid barriers cheaper and the big levels slower
+			grid = std::min(grid, std::max(forced_grid, 1u));
 		HD_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_edit_fused, dim3(grid), dim3(kFusedThreads), params, 0, p->stream));
 		g_launches.fetch_add(1, std::memory_order_relaxed);
 	} else {
