@@ -1018,61 +1018,232 @@ __global__ void __launch_bounds__(kBlock) k_leaf_lane(Geometry g, const uint32_t
 // Only CHANGED, non-empty leaves get a slot in the (compact) leaf level that the find-or-insert then works on: the cfg3 batch
 // visits 138.6 M leaves and changes a tenth of them, so the dedup / bucket-sort / resolve kernels of the leaf level shrink
 // with it.  Unchanged and emptied leaves report straight into the parent's child_new.
-__global__ void __launch_bounds__(kBlock) k_down_leaf(Geometry g, const uint32_t *__restrict__ words,
-                                                      const hd_edit_desc *__restrict__ edits, const uint32_t *__restrict__ filled,
-                                                      LevelView in, LevelView out, DevCounters *ctr) {
-	__shared__ uint32_t s_alloc[2 * (kMaxWarps + 1)];
-	const uint32_t level = g.node_levels - 2u, n8 = in.count() * 8u, filled_leaf = filled[g.node_levels - 1u];
-	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t item = t >> 3, c = t & 7u;
-	const bool valid = t < n8;
-	bool evaluated = false, changed = false;
-	uint32_t n0 = 0u, n1 = 0u, base_ptr = kNull;
-	if (valid) {
-		const uint32_t cur = in.cur[item];
-		uint32_t child = kNull;
-		if (cur != kNull) {
-			const uint32_t mask = words[cur];
-			if (mask >> c & 1u)
-				child = words[cur + 1u + __popc(mask & ((1u << c) - 1u))];
+// Round 2, second pass.  ncu on the cfg3 batch: 5.3 G warp instructions, issue slots 76 % busy, DRAM 8 % — the kernel is bound
+// by the instructions of the CLASSIFICATION (EditNode of every child against every edit of the parent's list, ~45 instructions
+// each, 277 M (item, child) pairs), not by the leaves (compacting the proceeding pairs so that leaf_apply ran with full warps
+// raised the lanes per instruction from 20.7 to 27.5 and saved nothing).  So a thread now takes a whole ITEM: the eight
+// children share three planes per axis, edit_node8 forms the per-axis terms once and classifies all eight (~8 instructions
+// per child and edit), and the list is walked once instead of eight times.  The proceeding children are then compacted
+// through shared memory and the CTA's threads apply the surviving edits to one leaf each, with full warps.
+// An item's eight children against its edit list (<= 32 entries), last edit first — filter_list's semantics for all eight at
+// once: the last kFill / kClear replaces the child and ends its scan (kProceed edits before it are dropped), kNotAffected
+// edits are ignored, and leading edits that cannot change the child in its base state (is_noop) are dropped.
+// curc[c] comes in as the child's old pointer and goes out as its base pointer; keep[c] = surviving edits (bit j = list[j]).
+__device__ __forceinline__ void classify_children(const hd_edit_desc *__restrict__ edits, const uint32_t *__restrict__ list,
+                                                  uint32_t len, uint32_t bits, uint32_t x, uint32_t y, uint32_t z,
+                                                  uint32_t filled_ptr, uint32_t (&curc)[8], uint32_t (&keep)[8]) {
+#pragma unroll
+	for (int c = 0; c < 8; ++c)
+		keep[c] = 0u;
+	uint32_t open = 0xFFu; // children whose scan has not met a terminal edit yet
+	for (int j = int(len) - 1; j >= 0 && open; --j) {
+		const uint32_t types = edit_node8(edits[list[j]], bits, x, y, z);
+#pragma unroll
+		for (int c = 0; c < 8; ++c) {
+			const uint32_t ty = (types >> (2 * c)) & 3u;
+			if ((open >> c & 1u) && ty != kNotAffected) {
+				if (ty == kProceed)
+					keep[c] |= 1u << j;
+				else
+					curc[c] = ty == kFill ? filled_ptr : kNull, open &= ~(1u << c);
+			}
 		}
-		uint32_t x, y, z;
+	}
+#pragma unroll
+	for (int c = 0; c < 8; ++c)
+		if (keep[c] && (curc[c] == kNull || curc[c] == filled_ptr))
+			while (keep[c] && is_noop(edits[list[__ffs(keep[c]) - 1]].kind, curc[c], filled_ptr))
+				keep[c] &= keep[c] - 1u;
+}
+
+// Top-down expansion of one inner level with a thread per ITEM (batches without a terrain edit; items whose list is longer
+// than 32 entries are left to k_down_long / k_down_huge): what phase_down does with a thread per (item, child) pair, with
+// the classification shared between the eight children (classify_children) and ONE pair of atomics per CTA for the
+// queue slots and list entries of everything the CTA's items produce.
+constexpr uint32_t kDownItems = 128;
+__global__ void __launch_bounds__(kDownItems) k_down_items(Geometry g, uint32_t level, const uint32_t *__restrict__ words,
+                                                           const hd_edit_desc *__restrict__ edits,
+                                                           const uint32_t *__restrict__ filled, LevelView in, LevelView out,
+                                                           DevCounters *ctr, uint32_t *items_ctr, uint32_t *entries_ctr) {
+	__shared__ uint32_t s_wi[kMaxWarps + 1], s_we[kMaxWarps + 1], s_base[2];
+	const uint32_t n = in.count(), bits = g.voxel_level() - (level + 1u), filled_ptr = filled[level + 1u];
+	const uint32_t item = blockIdx.x * kDownItems + threadIdx.x;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = kDownItems >> 5;
+	uint32_t curc[8], keep[8];
+#pragma unroll
+	for (int c = 0; c < 8; ++c)
+		curc[c] = kNull, keep[c] = 0u;
+	uint32_t x = 0, y = 0, z = 0, want = 0u, n_entries = 0u;
+	const uint32_t *list = nullptr;
+	if (item < n && in.list_len[item] <= 32u) {
+		const uint32_t cur = in.cur[item];
+		if (cur != kNull) { // get_unpacked_node_array, NodePool.hpp:278-309
+			const uint32_t mask = words[cur];
+			uint32_t k = 1u;
+#pragma unroll
+			for (int c = 0; c < 8; ++c)
+				if (mask >> c & 1u)
+					curc[c] = words[cur + k++];
+		}
 		unpack_pos(in.pos[item], x, y, z);
-		x = (x << 1) | (c & 1u), y = (y << 1) | ((c >> 1) & 1u), z = (z << 1) | ((c >> 2) & 1u);
-		const uint32_t *list = in.lists + in.list_off[item];
-		const uint32_t len = in.list_len[item];
-		const Filtered f = filter_list<false>(edits, list, len, g.voxel_level() - (level + 1u), x, y, z, child, filled_leaf);
-		base_ptr = f.cur;
-		if (f.count == 0u)
-			in.child_new[size_t(item) * 8u + c] = f.cur;
-		else {
-			evaluated = true;
+		list = in.lists + in.list_off[item];
+		classify_children(edits, list, in.list_len[item], bits, x, y, z, filled_ptr, curc, keep);
+#pragma unroll
+		for (int c = 0; c < 8; ++c) {
+			if (keep[c])
+				want |= 1u << c, n_entries += __popc(keep[c]);
+			else
+				in.child_new[size_t(item) * 8u + c] = curc[c];
+		}
+	}
+	// ---- queue slots and list entries for the CTA: warp scans, one pair of atomics ----
+	const uint32_t n_items = __popc(want);
+	uint32_t ii = n_items, ie = n_entries;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, ii, d), b = __shfl_up_sync(0xFFFFFFFFu, ie, d);
+		if (lane >= uint32_t(d))
+			ii += a, ie += b;
+	}
+	if (lane == 31u)
+		s_wi[warp] = ii, s_we[warp] = ie;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t ti = 0, te = 0;
+		for (uint32_t w = 0; w < nwarps; ++w) {
+			const uint32_t a = s_wi[w], b = s_we[w];
+			s_wi[w] = ti, s_we[w] = te;
+			ti += a, te += b;
+		}
+		uint32_t bi = 0, be = 0;
+		if (ti) {
+			bi = atomicAdd(items_ctr, ti);
+			be = atomicAdd(entries_ctr, te);
+			if (bi + ti > out.cap || be + te > out.cap_entries)
+				ctr->error = 1, bi = 0xFFFFFFFFu;
+		}
+		s_base[0] = bi, s_base[1] = be;
+	}
+	__syncthreads();
+	if (!want || s_base[0] == 0xFFFFFFFFu)
+		return;
+	uint32_t slot = s_base[0] + s_wi[warp] + ii - n_items, entry = s_base[1] + s_we[warp] + ie - n_entries;
+#pragma unroll
+	for (int c = 0; c < 8; ++c) {
+		if (!(want >> c & 1u))
+			continue;
+		out.cur[slot] = curc[c];
+		out.pos[slot] = pack_pos((x << 1) | uint32_t(c & 1), (y << 1) | uint32_t((c >> 1) & 1), (z << 1) | uint32_t(c >> 2)); // NodeCoord.hpp:18-28
+		out.parent[slot] = (item << 3) | uint32_t(c);
+		out.list_off[slot] = entry;
+		out.list_len[slot] = __popc(keep[c]);
+		for (uint32_t kp = keep[c]; kp; kp &= kp - 1u)
+			out.lists[entry++] = list[__ffs(kp) - 1];
+		in.child_new[size_t(item) * 8u + c] = kPending;
+		++slot;
+	}
+}
+
+constexpr uint32_t kLeafItems = 128; // items (threads) per CTA of k_down_leaf: up to 1 024 proceeding leaves in shared memory
+__global__ void __launch_bounds__(kLeafItems) k_down_leaf(Geometry g, const uint32_t *__restrict__ words,
+                                                          const hd_edit_desc *__restrict__ edits, const uint32_t *__restrict__ filled,
+                                                          LevelView in, LevelView out, DevCounters *ctr) {
+	__shared__ uint32_t s_alloc[2 * (kMaxWarps + 1)];
+	__shared__ uint32_t s_pair[kLeafItems * 8], s_cur[kLeafItems * 8], s_keep[kLeafItems * 8], s_warp[kMaxWarps + 1];
+	const uint32_t level = g.node_levels - 2u, n = in.count(), filled_leaf = filled[g.node_levels - 1u];
+	const uint32_t bits = g.voxel_level() - (level + 1u);
+	const uint32_t item = blockIdx.x * kLeafItems + threadIdx.x;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = kLeafItems >> 5;
+	// ---- phase 1: classify the item's eight children against its edit list (classify_children) ----
+	uint32_t curc[8], keep[8];
+#pragma unroll
+	for (int c = 0; c < 8; ++c)
+		curc[c] = kNull, keep[c] = 0u;
+	uint32_t x = 0, y = 0, z = 0, want = 0u; // want: children with surviving edits
+	const uint32_t *list = nullptr;
+	if (item < n) {
+		const uint32_t cur = in.cur[item];
+		if (cur != kNull) { // get_unpacked_node_array, NodePool.hpp:278-309
+			const uint32_t mask = words[cur];
+			uint32_t k = 1u;
+#pragma unroll
+			for (int c = 0; c < 8; ++c)
+				if (mask >> c & 1u)
+					curc[c] = words[cur + k++];
+		}
+		unpack_pos(in.pos[item], x, y, z);
+		list = in.lists + in.list_off[item];
+		classify_children(edits, list, in.list_len[item], bits, x, y, z, filled_leaf, curc, keep);
+#pragma unroll
+		for (int c = 0; c < 8; ++c) {
+			if (keep[c])
+				want |= 1u << c;
+			else
+				in.child_new[size_t(item) * 8u + c] = curc[c];
+		}
+	}
+	// ---- compaction of the proceeding children of the CTA ----
+	const uint32_t mine = __popc(want);
+	uint32_t incl = mine;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+		if (lane >= uint32_t(d))
+			incl += v;
+	}
+	if (lane == 31u)
+		s_warp[warp] = incl;
+	__syncthreads();
+	uint32_t before = 0u, n_work = 0u;
+	for (uint32_t w = 0; w < nwarps; ++w) {
+		const uint32_t k = s_warp[w];
+		before += w < warp ? k : 0u, n_work += k;
+	}
+	{
+		uint32_t at = before + incl - mine;
+#pragma unroll
+		for (int c = 0; c < 8; ++c)
+			if (want >> c & 1u)
+				s_pair[at] = (item << 3) | uint32_t(c), s_cur[at] = curc[c], s_keep[at] = keep[c], ++at;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0 && n_work)
+		atomicAdd(&ctr->stats[1], (unsigned long long)n_work);
+	// ---- phase 2: one proceeding leaf per thread and trip (EditVoxel, NodePool.hpp:319-343) ----
+	for (uint32_t k0 = 0; k0 < n_work; k0 += kLeafItems) { // uniform trip count: alloc_item synchronises the CTA
+		const uint32_t k = k0 + threadIdx.x;
+		bool changed = false;
+		uint32_t n0 = 0u, n1 = 0u, base_ptr = kNull, pair = 0u;
+		if (k < n_work) {
+			pair = s_pair[k], base_ptr = s_cur[k];
+			const uint32_t it = pair >> 3, c = pair & 7u;
+			uint32_t px, py, pz;
+			unpack_pos(in.pos[it], px, py, pz);
+			px = (px << 1) | (c & 1u), py = (py << 1) | ((c >> 1) & 1u), pz = (pz << 1) | ((c >> 2) & 1u); // NodeCoord.hpp:18-28
+			const uint32_t *lst = in.lists + in.list_off[it];
 			uint32_t w0 = 0u, w1 = 0u;
-			if (f.cur != kNull) {
-				const uint2 w = *reinterpret_cast<const uint2 *>(words + f.cur);
+			if (base_ptr != kNull) {
+				const uint2 w = *reinterpret_cast<const uint2 *>(words + base_ptr);
 				w0 = w.x, w1 = w.y;
 			}
 			n0 = w0, n1 = w1;
-			for (uint32_t keep = f.keep; keep; keep &= keep - 1u)
-				leaf_apply(edits[list[__ffs(keep) - 1]], x << 2, y << 2, z << 2, n0, n1);
+			for (uint32_t kp = s_keep[k]; kp; kp &= kp - 1u)
+				leaf_apply(edits[lst[__ffs(kp) - 1]], px << 2, py << 2, pz << 2, n0, n1);
 			if (n0 == w0 && n1 == w1)
-				in.child_new[size_t(item) * 8u + c] = f.cur; // unchanged (edit_leaf tail, NodePool.hpp:336-342)
+				in.child_new[pair] = base_ptr; // unchanged (edit_leaf tail, NodePool.hpp:336-342)
 			else if ((n0 | n1) == 0u)
-				in.child_new[size_t(item) * 8u + c] = kNull;
+				in.child_new[pair] = kNull;
 			else
 				changed = true;
 		}
-	}
-	const uint32_t n_eval = __syncthreads_count(evaluated);
-	if (threadIdx.x == 0 && n_eval)
-		atomicAdd(&ctr->stats[1], (unsigned long long)n_eval);
-	uint32_t slot, entry_off;
-	if (alloc_item(ctr, &ctr->next_items, &ctr->next_entries, changed, 0u, out.cap, out.cap_entries, slot, entry_off, s_alloc)) {
-		out.cur[slot] = base_ptr; // the bucket-full fallback of upsert_leaf (NodePool.hpp:195)
-		out.parent[slot] = (item << 3) | c;
-		out.state[slot] = 1; // every leaf of the compact level is a candidate
-		*reinterpret_cast<uint2 *>(out.cand + size_t(slot) * 2u) = make_uint2(n0, n1);
-		in.child_new[size_t(item) * 8u + c] = kPending;
+		uint32_t slot, entry_off;
+		if (alloc_item(ctr, &ctr->next_items, &ctr->next_entries, changed, 0u, out.cap, out.cap_entries, slot, entry_off, s_alloc)) {
+			out.cur[slot] = base_ptr; // the bucket-full fallback of upsert_leaf (NodePool.hpp:195)
+			out.parent[slot] = pair;  // (item << 3) | child
+			out.state[slot] = 1; // every leaf of the compact level is a candidate
+			*reinterpret_cast<uint2 *>(out.cand + size_t(slot) * 2u) = make_uint2(n0, n1);
+			in.child_new[pair] = kPending;
+		}
 	}
 }
 
@@ -2296,10 +2467,12 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 		// reset per-level cursors (stats keep accumulating)
 		HD_CUDA_TRY(cudaMemsetAsync(&s->ctr->next_items, 0, 4 * sizeof(uint32_t), st));
 		static const bool fuse_off = getenv("HD_EDIT_LEAF") != nullptr; // "half" / "lane": the separate leaf kernels
+		static const bool pair_threads = getenv("HD_EDIT_DOWN_PAIRS") != nullptr; // the thread-per-(item, child) k_down, for A/B runs
 		if (l + 2 == L && !terrain && !long_lists && !fuse_off) {
 			// ---- last inner level + leaves fused (k_down_leaf): the leaf level holds the CHANGED leaves only ----
 			HD_CUDA_TRY(out.init_compact_leaves(uint32_t(cap), st));
-			k_down_leaf<<<grid_for(cap), kBlock, 0, st>>>(g, p->words, edits_dev, s->filled_dev, in.v, out.v, s->ctr);
+			k_down_leaf<<<(in.v.n + kLeafItems - 1u) / kLeafItems, kLeafItems, 0, st>>>(g, p->words, edits_dev, s->filled_dev, in.v, out.v,
+			                                                                          s->ctr);
 			HD_LAUNCH_CHECK();
 			rs = read_counters(p, host);
 			if (rs != HD_OK)
@@ -2321,9 +2494,12 @@ static hd_status edit_batch_impl(hd_pool *p, uint32_t root_in, const hd_edit_des
 		if (terrain)
 			k_down<true><<<grid_for(uint64_t(in.v.n) * 8), kBlock, 0, st>>>(g, l, p->words, edits_dev, s->filled_dev, in.v, out.v,
 			                                                                s->ctr, &s->ctr->next_items, &s->ctr->next_entries);
-		else
+		else if (pair_threads)
 			k_down<false><<<grid_for(uint64_t(in.v.n) * 8), kBlock, 0, st>>>(g, l, p->words, edits_dev, s->filled_dev, in.v, out.v,
 			                                                                 s->ctr, &s->ctr->next_items, &s->ctr->next_entries);
+		else // a thread per item, the eight children classified together
+			k_down_items<<<(in.v.n + kDownItems - 1u) / kDownItems, kDownItems, 0, st>>>(
+			    g, l, p->words, edits_dev, s->filled_dev, in.v, out.v, s->ctr, &s->ctr->next_items, &s->ctr->next_entries);
 		HD_LAUNCH_CHECK();
 		if (long_lists) {
 			k_down_long<<<grid_for(uint64_t(in.v.n) * 8 * 32), kBlock, 0, st>>>(g, l, p->words, edits_dev, s->filled_dev,
