@@ -2056,11 +2056,32 @@ __global__ void __launch_bounds__(kGroupThreads) k_upsert_grouped(Geometry g, ui
 		tsize <<= 1;
 	const uint32_t tmask = tsize - 1u;
 	const bool indexed = is_leaf || fast_scan;
+	// The first chunk's candidates are fetched BEFORE the image is staged: order -> candidate words is a chain of two
+	// dependent global round trips that used to start only after the staging and the index build, and a CTA of the
+	// 8^3-node level lives for a handful of such round trips (half a million CTAs with a dozen candidates each: ncu shows
+	// the kernel waiting on barriers and loads, not issuing).
+	// Order of issue: the candidate's index (order[]) first, then the staging loads, then — with the index back — ALL `stride`
+	// words of the candidate without looking at its header (a load that waits for the header would stall the thread before
+	// the next one is issued), and the index build runs in the shadow of those loads.
+	uint32_t pre_item = 0, pre_w[9];
+#pragma unroll
+	for (uint32_t i = 0; i < 9u; ++i)
+		pre_w[i] = 0u;
+	const bool pre = indexed && threadIdx.x < cnt;
+	if (pre)
+		pre_item = order[first + threadIdx.x];
 	{
 		const uint4 *src = reinterpret_cast<const uint4 *>(words + base);
 		uint4 *dst = reinterpret_cast<uint4 *>(img);
 		for (uint32_t i = threadIdx.x; i < (bw + 3u) / 4u; i += kGroupThreads)
 			dst[i] = src[i];
+		if (pre) {
+			const uint32_t *me = cand + size_t(pre_item) * stride;
+#pragma unroll
+			for (uint32_t i = 0; i < 9u; ++i)
+				if (i < stride)
+					pre_w[i] = me[i];
+		}
 		if (indexed) {
 			uint4 *t4 = reinterpret_cast<uint4 *>(tab);
 			for (uint32_t i = threadIdx.x; i < tsize / 4u; i += kGroupThreads)
@@ -2083,14 +2104,34 @@ __global__ void __launch_bounds__(kGroupThreads) k_upsert_grouped(Geometry g, ui
 					slot = (slot + 1u) & tmask;
 			}
 		} else {
-			// a word <= 0xFF inside the used region is always a node header (child pointers are >= 256 here, padding is 0)
-			for (uint32_t q = threadIdx.x; q < bw; q += kGroupThreads) {
-				const uint32_t hw = img[q];
-				if (hw - 1u >= 0xFFu)
-					continue;
-				const uint32_t nw = 1u + __popc(hw);
-				if (q + nw > bw)
-					continue;
+			// a word <= 0xFF inside the used region is always a node header (child pointers are >= 256 here, padding is 0).
+			// One word in six is a header, so testing and hashing in the same loop ran the hash (the expensive part) at five
+			// lanes of 32 — ncu: 10.7 lanes per instruction over the kernel.  The header positions are compacted first and
+			// hashed by full warps.
+			uint16_t *s_hdr = reinterpret_cast<uint16_t *>(tab + wpb); // wpb / 2 entries of the dynamic allocation
+			__shared__ uint32_t s_nhdr;
+			if (threadIdx.x == 0)
+				s_nhdr = 0u;
+			__syncthreads();
+			for (uint32_t q0 = 0; q0 < bw; q0 += kGroupThreads) {
+				const uint32_t q = q0 + threadIdx.x;
+				bool hdr = false;
+				if (q < bw) {
+					const uint32_t hw = img[q];
+					hdr = hw - 1u < 0xFFu && q + 1u + __popc(hw) <= bw;
+				}
+				const uint32_t votes = __ballot_sync(0xFFFFFFFFu, hdr);
+				uint32_t at = 0u;
+				if (lane == 0 && votes)
+					at = atomicAdd(&s_nhdr, uint32_t(__popc(votes)));
+				at = __shfl_sync(0xFFFFFFFFu, at, 0);
+				if (hdr)
+					s_hdr[at + __popc(votes & ((1u << lane) - 1u))] = uint16_t(q);
+			}
+			__syncthreads();
+			const uint32_t nh = s_nhdr;
+			for (uint32_t i = threadIdx.x; i < nh; i += kGroupThreads) {
+				const uint32_t q = s_hdr[i], nw = 1u + __popc(img[q]);
 				uint32_t slot = image_hashn(img + q, nw) & tmask;
 				while (atomicCAS(&tab[slot], 0u, q + 1u) != 0u)
 					slot = (slot + 1u) & tmask;
@@ -2109,13 +2150,22 @@ __global__ void __launch_bounds__(kGroupThreads) k_upsert_grouped(Geometry g, ui
 			uint32_t item = 0, nw = 0, found = kMiss;
 			uint32_t w[9];
 			if (c < cnt) {
-				item = order[first + c];
-				const uint32_t *me = cand + size_t(item) * stride;
-				w[0] = me[0], w[1] = me[1];
-				nw = is_leaf ? 2u : 1u + __popc(w[0] & 0xFFu);
+				if (c0 == 0u) { // fetched while the image was staged; words behind the node's own are ignored
+					item = pre_item;
+					w[0] = pre_w[0], w[1] = pre_w[1];
+					nw = is_leaf ? 2u : 1u + __popc(w[0] & 0xFFu);
 #pragma unroll
-				for (uint32_t i = 2; i < 9u; ++i)
-					w[i] = i < nw ? me[i] : 0u;
+					for (uint32_t i = 2; i < 9u; ++i)
+						w[i] = i < nw ? pre_w[i] : 0u;
+				} else {
+					item = order[first + c];
+					const uint32_t *me = cand + size_t(item) * stride;
+					w[0] = me[0], w[1] = me[1];
+					nw = is_leaf ? 2u : 1u + __popc(w[0] & 0xFFu);
+#pragma unroll
+					for (uint32_t i = 2; i < 9u; ++i)
+						w[i] = i < nw ? me[i] : 0u;
+				}
 				uint32_t slot = (is_leaf ? image_hash2(w[0], w[1]) : image_hashn_reg(w, nw)) & tmask;
 				for (uint32_t v; (v = tab[slot]) != 0u; slot = (slot + 1u) & tmask) {
 					const uint32_t q = v - 1u;
@@ -2304,10 +2354,11 @@ static hd_status run_upsert(hd_pool *p, uint32_t level, uint32_t n, uint32_t str
 		k_bucket_scatter<<<grid_for(n), kBlock, 0, p->stream>>>(n, state, bkt, offset, count, order);
 		HD_LAUNCH_CHECK();
 		// ...which ends up holding the per-bucket candidate count again
-		// dynamic shared memory: the bucket image + its content index (8 bytes per bucket word: 16 KB for 2 048-word buckets)
-		const size_t gsm = size_t(p->geo.words_per_bucket()) * 8;
+		// dynamic shared memory: the bucket image, its content index and the header positions (9 bytes per bucket word: 18 KB
+		// for 2 048-word buckets)
+		const size_t gsm = size_t(p->geo.words_per_bucket()) * 9;
 		if (!p->grouped_smem_attr && gsm > 48u * 1024u) { // a per-device attribute: kept in the pool, not in a process static
-			HD_CUDA_TRY(cudaFuncSetAttribute(k_upsert_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGroupMaxWords) * 8));
+			HD_CUDA_TRY(cudaFuncSetAttribute(k_upsert_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGroupMaxWords) * 9));
 			p->grouped_smem_attr = true;
 		}
 		k_upsert_grouped<<<nb, kGroupThreads, gsm, p->stream>>>(
