@@ -309,6 +309,11 @@ hd_status hd_trace_table_info(hd_pool *pool, uint32_t *root, uint32_t *levels, u
  * [2^-51, 2^51), the unchecked square root over every float in [2^-100, 2^100), x / D for every 0 <= x <= D, D in {255, 63, 31,
  * 7, 3}, and fma(h, c, t) == h * c + t for sampled power-of-two h.  *mismatches = number of differing results (0 = exact). */
 hd_status hd_selftest_exact_arith(int device, uint64_t *mismatches);
+/* The batched edit classifies the eight children of a node with shared per-axis terms (editors.cuh: edit_node8) where the
+ * reference calls EditNode once per child (NodePool.hpp:345-360, editors src/main.cpp:35-46,77-106): n_cases pseudo-random editors
+ * and nodes around the decision boundaries (touching boxes, near and far spheres, 32- and 64-bit paths, every level) through both;
+ * *mismatches = nodes whose eight classifications differ (0 = identical). */
+hd_status hd_selftest_edit_node8(int device, uint32_t n_cases, uint64_t *mismatches);
 
 #ifdef __cplusplus
 }

@@ -322,3 +322,9 @@ def test_mid_size_batches_one_launch(oracle, hd):
         dev = check_equal(oracle, hd, cfg, base + edits, batches=[1, n])[0]
         assert dev.last_stats["path"] in ("fused", "graph"), (n, dev.last_stats)
         dev.close()
+
+
+def test_edit_node8_equals_eight_edit_node_calls(hd):
+    """The shared-plane classification of a node's eight children (edit_node8) returns what EditNode returns for each child,
+    on 64 M pseudo-random editor / node pairs placed around the decision boundaries."""
+    assert hd.api.selftest_edit_node8(1 << 26, 0) == 0

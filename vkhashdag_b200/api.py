@@ -68,7 +68,7 @@ SYMBOLS = [
     "hd_pool_load", "hd_gc", "hd_trace_submit", "hd_trace_collect", "hd_beam_dev",
     "hd_trace_with_beam_dev", "hd_trace_with_beam", "hd_color_config", "hd_color_root", "hd_color_leaf_level",
     "hd_color_sizes", "hd_color_read", "hd_edit_color", "hd_edit_last_path",
-    "hd_tile_shard_locate", "hd_pool_read_subtree", "hd_host_alloc", "hd_host_free", "hd_selftest_exact_arith", "hd_trace_table_info",
+    "hd_tile_shard_locate", "hd_pool_read_subtree", "hd_host_alloc", "hd_host_free", "hd_selftest_exact_arith", "hd_trace_table_info", "hd_selftest_edit_node8",
 ]
 
 
@@ -151,6 +151,7 @@ def lib():
     L.hd_host_free.argtypes = [vp]
     L.hd_kernel_launches.restype = u64
     L.hd_selftest_exact_arith.argtypes = [ci, C.POINTER(u64)]
+    L.hd_selftest_edit_node8.argtypes = [ci, u32, C.POINTER(u64)]
     L.hd_trace_table_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
     _lib = L
     return L
@@ -181,6 +182,14 @@ def selftest_exact_arith(device=0):
     """Mismatches between the trace kernel's exact-arithmetic shortcuts and the IEEE operations they replace (0 = exact)."""
     n = C.c_uint64(0)
     _check(lib().hd_selftest_exact_arith(int(device), C.byref(n)))
+    return int(n.value)
+
+
+def selftest_edit_node8(n_cases=1 << 24, device=0):
+    """Nodes (of n_cases pseudo-random editor / node pairs) whose eight child classifications differ between edit_node8 and
+    eight edit_node calls (0 = identical)."""
+    n = C.c_uint64(0)
+    _check(lib().hd_selftest_edit_node8(int(device), int(n_cases), C.byref(n)))
     return int(n.value)
 
 

@@ -2859,6 +2859,42 @@ static hd_status fast_edit(hd_pool *p, uint32_t root_in, const hd_edit_desc *edi
 	return fast_edit_end(p, root_out, stats, handled);
 }
 
+// hd_selftest_edit_node8: edit_node8 against eight edit_node calls on pseudo-random editors and nodes that stress the
+// boundaries — boxes that touch / contain / straddle the editor, spheres around and far from the node (the 32-bit and the
+// 64-bit paths), radii from 0 to beyond the world, every level from leaves (bits 2) to 2^16-voxel nodes, coordinates up to 2^21.
+__global__ void k_selftest_edit_node8(uint32_t n, unsigned long long *bad) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n)
+		return;
+	uint32_t r = fmix32(t * 2654435761u + 0x9E3779B9u);
+	auto next = [&]() { return r = fmix32(r + 0x85EBCA6Bu); };
+	const uint32_t bits = 2u + next() % 15u;            // child level: 4 .. 65 536 voxels per node edge
+	const uint32_t span = 21u - (bits + 1u);              // parent positions keep every coordinate below 2^21
+	const uint32_t x = next() & ((1u << span) - 1u), y = next() & ((1u << span) - 1u), z = next() & ((1u << span) - 1u);
+	const uint32_t s = 1u << bits, L[3] = {(x << 1) << bits, (y << 1) << bits, (z << 1) << bits};
+	hd_edit_desc d{};
+	d.kind = next() % 3u; // AABB, sphere fill, sphere dig
+	const uint32_t mode = next() % 4u;
+	for (int a = 0; a < 3; ++a) {
+		// anchor near one of the node's planes (mode 0-2) or anywhere in the world (mode 3), jittered by up to +-2 voxels / a node
+		const uint32_t plane = L[a] + s * (next() % 3u);
+		const int32_t jitter = mode == 0u ? int32_t(next() % 5u) - 2 : mode == 1u ? int32_t(next() % (2u * s + 1u)) - int32_t(s) : 0;
+		uint32_t p = mode == 3u ? next() & 0x1FFFFFu : uint32_t(max(0, int32_t(plane) + jitter));
+		d.p0[a] = p;
+		d.p1[a] = p + (next() % 4u == 0u ? 0u : 1u + next() % (3u * s));
+	}
+	const uint32_t rk = next() % 6u;
+	const uint64_t rad = rk == 0u ? 0ull : rk == 1u ? uint64_t(next() % 8u) : rk == 2u ? uint64_t(next() % (4u * s)) : rk == 3u ? uint64_t(s)
+	                   : rk == 4u ? uint64_t(next() & 0x3FFFFFu) : uint64_t(next());
+	d.r2 = rk == 3u ? rad * rad * (next() % 4u) : rad * rad + next() % 3u;
+	const uint32_t got = edit_node8(d, bits, x, y, z);
+	uint32_t want = 0u;
+	for (uint32_t c = 0; c < 8u; ++c)
+		want |= uint32_t(edit_node<false>(d, bits, (x << 1) | (c & 1u), (y << 1) | ((c >> 1) & 1u), (z << 1) | (c >> 2))) << (2u * c);
+	if (got != want)
+		atomicAdd(bad, 1ull);
+}
+
 } // namespace hd
 
 using namespace hd;
@@ -2907,6 +2943,22 @@ hd_status hd_edit_batch(hd_pool *p, uint32_t root_in, const hd_edit_desc *edits,
 }
 
 uint32_t hd_edit_last_path(const hd_pool *p) { return p && p->edit ? p->edit->last_path : 0u; }
+
+hd_status hd_selftest_edit_node8(int device, uint32_t n_cases, uint64_t *mismatches) {
+	if (!mismatches)
+		return HD_ERR_INVALID;
+	HD_CUDA_TRY(cudaSetDevice(device));
+	unsigned long long *bad = nullptr;
+	HD_CUDA_TRY(cudaMalloc(&bad, sizeof(*bad)));
+	ScopeExit guard{[&]() { cudaFree(bad); }};
+	HD_CUDA_TRY(cudaMemset(bad, 0, sizeof(*bad)));
+	k_selftest_edit_node8<<<(n_cases + 255u) / 256u, 256>>>(n_cases, bad);
+	HD_LAUNCH_CHECK();
+	unsigned long long host = 0;
+	HD_CUDA_TRY(cudaMemcpy(&host, bad, sizeof(host), cudaMemcpyDeviceToHost));
+	*mismatches = host;
+	return HD_OK;
+}
 
 hd_status hd_upsert_nodes(hd_pool *p, uint32_t level, const uint32_t *nodes, uint32_t words_each, uint32_t n,
                           uint32_t *out_ptrs) {
