@@ -1012,9 +1012,9 @@ __global__ void __launch_bounds__(kBlock) k_leaf_lane(Geometry g, const uint32_t
 	}
 }
 
-// Last inner level and the leaf pass in ONE kernel (batches without a terrain edit, lists of <= 32 entries): the thread
-// that classifies child c of an item of level L-2 (EditNode on the leaf's box, filter_list) goes on to apply the surviving
-// edits to that leaf itself (leaf_apply) instead of writing a 24-byte queue record plus list for k_leaf_lane to read back.
+// Last inner level and the leaf pass in ONE kernel (batches without a terrain edit, lists of <= 32 entries): the children of
+// the items of level L-2 are classified (EditNode on each leaf's box) and the surviving edits applied to the leaves
+// (leaf_apply) right here, instead of writing a 24-byte queue record plus list per leaf for k_leaf_lane to read back.
 // Only CHANGED, non-empty leaves get a slot in the (compact) leaf level that the find-or-insert then works on: the cfg3 batch
 // visits 138.6 M leaves and changes a tenth of them, so the dedup / bucket-sort / resolve kernels of the leaf level shrink
 // with it.  Unchanged and emptied leaves report straight into the parent's child_new.
