@@ -205,6 +205,7 @@ def test_staged_top_levels_equal_the_pool_path(oracle, hd):
 
 
 def _staged_top_levels(oracle, hd):
+    import os
     cfg = abi.default_config(level_count=10, top_level_count=9)
     opool = oracle.pool(cfg)
     roots = [opool.edit_batch(NULL, [abi.terrain(cfg.voxel_level)] + abi.random_spheres(30, cfg.voxel_level, seed=2, rmin=8, rmax=80))]
@@ -228,8 +229,9 @@ def _staged_top_levels(oracle, hd):
                     sh = dev.Trace(P, want=("rgba8",), shard=(64, 64, 1, 2))
                     ref_sh = oracle_shard(exp["rgba8"], P, (64, 64, 1, 2), dev)
                     assert np.array_equal(sh["rgba8"], ref_sh), (rnd, root, k, cam, "shard")
-            troot, tlevels, tnodes = dev.TraceTableInfo()   # the last frames of this root really read the table
-            assert troot == root and 1 <= tlevels <= cfg.node_levels - 2 and tnodes > tlevels, (troot, tlevels, tnodes)
+            if os.environ.get("HD_TRACE_VARIANT", "0") == "0":   # a forced A/B variant never stages anything
+                troot, tlevels, tnodes = dev.TraceTableInfo()   # the last frames of this root really read the table
+                assert troot == root and 1 <= tlevels <= cfg.node_levels - 2 and tnodes > tlevels, (troot, tlevels, tnodes)
         dev.Clear()                        # invalidates the table; the same pointers come back with the re-upload
         dev.UploadFrom(opool)
     dev.close()
