@@ -1288,10 +1288,13 @@ __global__ void __launch_bounds__(kBlock) k_assemble(const uint32_t *__restrict_
 }
 
 // In-batch dedup: one winner per distinct candidate content.  Thread per item.
+// bkt / count (optional): a winner also works out its bucket and counts itself there — what k_bucket_count does in a pass
+// of its own over the candidates' words, which this thread already holds.
 __global__ void __launch_bounds__(kBlock) k_dedup(uint32_t n, uint32_t stride, bool is_leaf,
                                                   const uint32_t *__restrict__ cand, uint8_t *state, uint32_t *winner,
                                                   uint32_t *table, uint32_t table_mask, const uint32_t *n_dev,
-                                                  const uint32_t *err_dev) {
+                                                  const uint32_t *err_dev, uint32_t *bkt = nullptr, uint32_t *count = nullptr,
+                                                  uint32_t bucket_mask = 0u) {
 	if (n_dev)
 		n = *err_dev ? 0u : *n_dev;
 	for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n; item += gridDim.x * blockDim.x) {
@@ -1309,6 +1312,11 @@ __global__ void __launch_bounds__(kBlock) k_dedup(uint32_t n, uint32_t stride, b
 				v = atomicCAS(&table[slot], 0u, item + 1u);
 				if (v == 0u) {
 					state[item] = 2; // winner
+					if (bkt) { // NodePool.hpp:163-164
+						const uint32_t b = (is_leaf ? hash_leaf(me[0], me[1]) : hash_inner(me, nw)) & bucket_mask;
+						bkt[item] = b;
+						atomicAdd(&count[b], 1u);
+					}
 					break;
 				}
 			}
@@ -1986,20 +1994,6 @@ constexpr uint32_t kMiss = 0xFFFFFFFDu;
 constexpr int kGroupThreads = 128;
 constexpr uint32_t kGroupMaxWords = 8192; // bucket images up to 32 KB are staged; larger buckets use k_upsert
 
-__global__ void __launch_bounds__(kBlock) k_bucket_count(Geometry g, uint32_t level, uint32_t n, uint32_t stride,
-                                                         const uint32_t *__restrict__ cand, const uint8_t *__restrict__ state,
-                                                         uint32_t *bkt, uint32_t *count) {
-	const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
-	if (item >= n || state[item] != 2)
-		return;
-	const bool is_leaf = level == g.node_levels - 1u;
-	const uint32_t *me = cand + size_t(item) * stride;
-	const uint32_t nw = is_leaf ? 2u : 1u + __popc(me[0] & 0xFFu);
-	const uint32_t h = is_leaf ? hash_leaf(me[0], me[1]) : hash_inner(me, nw);
-	const uint32_t b = h & ((1u << g.bucket_bits[level]) - 1u);
-	bkt[item] = b;
-	atomicAdd(&count[b], 1u);
-}
 __global__ void __launch_bounds__(kBlock) k_bucket_scatter(uint32_t n, const uint8_t *__restrict__ state,
                                                            const uint32_t *__restrict__ bkt, const uint32_t *__restrict__ offset,
                                                            uint32_t *fill, uint32_t *order) {
@@ -2328,25 +2322,27 @@ static hd_status run_upsert(hd_pool *p, uint32_t level, uint32_t n, uint32_t str
 	uint64_t tsize = 64;
 	while (tsize < uint64_t(n) * 2)
 		tsize <<= 1;
-	uint32_t *table = nullptr;
-	HD_CUDA_TRY(amalloc(&table, tsize, p->stream));
-	HD_CUDA_TRY(cudaMemsetAsync(table, 0, tsize * 4, p->stream));
-	k_dedup<<<grid_for(n), kBlock, 0, p->stream>>>(n, stride, is_leaf, cand, state, winner, table, uint32_t(tsize - 1), nullptr, nullptr);
-	HD_LAUNCH_CHECK();
-	HD_CUDA_TRY(cudaFreeAsync(table, p->stream));
 	// large batches: group the winners by bucket (one staged image and one writer per bucket); small ones and pools
 	// whose buckets do not fit a 32 KB image: one warp per winner with a lock-free append
 	static const int grouped_min = getenv("HD_EDIT_GROUPED_MIN") ? atoi(getenv("HD_EDIT_GROUPED_MIN")) : 16384;
 	const uint32_t nb = 1u << p->geo.bucket_bits[level];
-	if (n >= uint32_t(grouped_min) && p->geo.words_per_bucket() <= kGroupMaxWords) {
-		uint32_t *bkt = nullptr, *count = nullptr, *offset = nullptr, *order = nullptr;
+	const bool grouped = n >= uint32_t(grouped_min) && p->geo.words_per_bucket() <= kGroupMaxWords;
+	uint32_t *bkt = nullptr, *count = nullptr, *offset = nullptr, *order = nullptr;
+	if (grouped) { // the dedup pass counts the winners per bucket on its way
 		HD_CUDA_TRY(amalloc(&bkt, n, p->stream));
 		HD_CUDA_TRY(amalloc(&order, n, p->stream));
 		HD_CUDA_TRY(amalloc(&count, nb, p->stream));
 		HD_CUDA_TRY(amalloc(&offset, nb, p->stream));
 		HD_CUDA_TRY(cudaMemsetAsync(count, 0, size_t(nb) * 4, p->stream));
-		k_bucket_count<<<grid_for(n), kBlock, 0, p->stream>>>(p->geo, level, n, stride, cand, state, bkt, count);
-		HD_LAUNCH_CHECK();
+	}
+	uint32_t *table = nullptr;
+	HD_CUDA_TRY(amalloc(&table, tsize, p->stream));
+	HD_CUDA_TRY(cudaMemsetAsync(table, 0, tsize * 4, p->stream));
+	k_dedup<<<grid_for(n), kBlock, 0, p->stream>>>(n, stride, is_leaf, cand, state, winner, table, uint32_t(tsize - 1), nullptr, nullptr, bkt,
+	                                               count, nb - 1u);
+	HD_LAUNCH_CHECK();
+	HD_CUDA_TRY(cudaFreeAsync(table, p->stream));
+	if (grouped) {
 		hd_status ss = exclusive_scan(p, count, offset, nb);
 		if (ss != HD_OK)
 			return ss;
