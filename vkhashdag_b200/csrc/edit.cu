@@ -2023,6 +2023,24 @@ __device__ __forceinline__ uint32_t image_hashn_reg(const uint32_t (&w)[9], uint
 	return h ^ (h >> 15);
 }
 
+// The content index of a staged bucket holds 16-bit entries (node position + 1 <= kGroupMaxWords): the kernel's time follows the
+// number of CTAs an SM can hold (measured: +4 KB of shared memory per CTA = 11 -> 9 resident = +0.9 ms on the cfg3 batch), and
+// halving the table takes the CTA from 20.5 to 16.5 KB.  Insert = CAS on the 32-bit word that holds the half-word.
+__device__ __forceinline__ uint32_t index_insert16(uint16_t *tab, uint32_t slot, uint32_t val) { // 0: inserted, else the occupant
+	uint32_t *w = reinterpret_cast<uint32_t *>(tab) + (slot >> 1);
+	const uint32_t sh = (slot & 1u) << 4;
+	uint32_t old = *reinterpret_cast<volatile uint32_t *>(w);
+	for (;;) {
+		const uint32_t cur = (old >> sh) & 0xFFFFu;
+		if (cur)
+			return cur;
+		const uint32_t seen = atomicCAS(w, old, old | (val << sh));
+		if (seen == old)
+			return 0u;
+		old = seen;
+	}
+}
+
 __global__ void __launch_bounds__(kGroupThreads) k_upsert_grouped(Geometry g, uint32_t level, bool fast_scan, uint32_t stride,
                                                                   const uint32_t *__restrict__ cand,
                                                                   const uint32_t *__restrict__ fallback, uint32_t *result,
@@ -2044,7 +2062,7 @@ __global__ void __launch_bounds__(kGroupThreads) k_upsert_grouped(Geometry g, ui
 	// the 8^3-node level of the cfg3 batch a bucket holds ~600 words and a dozen candidates, and zeroing 2 048 slots word by
 	// word was the longest phase of the CTA.  Staging and zeroing move 16 bytes per thread (the bucket base is 8 KB-aligned
 	// and everything behind bw is zero).
-	uint32_t *tab = img + wpb;
+	uint16_t *tab = reinterpret_cast<uint16_t *>(img + wpb); // wpb half-words
 	uint32_t tsize = 64u;
 	while (tsize < bw)
 		tsize <<= 1;
@@ -2078,7 +2096,7 @@ __global__ void __launch_bounds__(kGroupThreads) k_upsert_grouped(Geometry g, ui
 		}
 		if (indexed) {
 			uint4 *t4 = reinterpret_cast<uint4 *>(tab);
-			for (uint32_t i = threadIdx.x; i < tsize / 4u; i += kGroupThreads)
+			for (uint32_t i = threadIdx.x; i < tsize / 8u; i += kGroupThreads) // tsize >= 64 half-words
 				t4[i] = make_uint4(0u, 0u, 0u, 0u);
 		}
 	}
@@ -2094,7 +2112,7 @@ __global__ void __launch_bounds__(kGroupThreads) k_upsert_grouped(Geometry g, ui
 				if ((w0 | w1) == 0u)
 					continue; // page-tail padding; an all-zero leaf is never stored (NodePool.hpp:337)
 				uint32_t slot = image_hash2(w0, w1) & tmask;
-				while (atomicCAS(&tab[slot], 0u, q + 1u) != 0u)
+				while (index_insert16(tab, slot, q + 1u) != 0u)
 					slot = (slot + 1u) & tmask;
 			}
 		} else {
@@ -2102,7 +2120,7 @@ __global__ void __launch_bounds__(kGroupThreads) k_upsert_grouped(Geometry g, ui
 			// One word in six is a header, so testing and hashing in the same loop ran the hash (the expensive part) at five
 			// lanes of 32 — ncu: 10.7 lanes per instruction over the kernel.  The header positions are compacted first and
 			// hashed by full warps.
-			uint16_t *s_hdr = reinterpret_cast<uint16_t *>(tab + wpb); // wpb / 2 entries of the dynamic allocation
+			uint16_t *s_hdr = tab + wpb; // wpb / 2 entries of the dynamic allocation, behind the index
 			__shared__ uint32_t s_nhdr;
 			if (threadIdx.x == 0)
 				s_nhdr = 0u;
@@ -2127,7 +2145,7 @@ __global__ void __launch_bounds__(kGroupThreads) k_upsert_grouped(Geometry g, ui
 			for (uint32_t i = threadIdx.x; i < nh; i += kGroupThreads) {
 				const uint32_t q = s_hdr[i], nw = 1u + __popc(img[q]);
 				uint32_t slot = image_hashn(img + q, nw) & tmask;
-				while (atomicCAS(&tab[slot], 0u, q + 1u) != 0u)
+				while (index_insert16(tab, slot, q + 1u) != 0u)
 					slot = (slot + 1u) & tmask;
 			}
 		}
@@ -2350,11 +2368,12 @@ static hd_status run_upsert(hd_pool *p, uint32_t level, uint32_t n, uint32_t str
 		k_bucket_scatter<<<grid_for(n), kBlock, 0, p->stream>>>(n, state, bkt, offset, count, order);
 		HD_LAUNCH_CHECK();
 		// ...which ends up holding the per-bucket candidate count again
-		// dynamic shared memory: the bucket image, its content index and the header positions (9 bytes per bucket word: 18 KB
-		// for 2 048-word buckets)
-		const size_t gsm = size_t(p->geo.words_per_bucket()) * 9;
+		// dynamic shared memory: the bucket image (4 bytes per bucket word), its content index (2) and the header positions (1):
+		// 14 KB for 2 048-word buckets
+		static const size_t gsm_pad = getenv("HD_EDIT_GROUPED_SMEM_PAD") ? size_t(atoi(getenv("HD_EDIT_GROUPED_SMEM_PAD"))) : 0; // residency experiments
+		const size_t gsm = size_t(p->geo.words_per_bucket()) * 7 + gsm_pad;
 		if (!p->grouped_smem_attr && gsm > 48u * 1024u) { // a per-device attribute: kept in the pool, not in a process static
-			HD_CUDA_TRY(cudaFuncSetAttribute(k_upsert_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGroupMaxWords) * 9));
+			HD_CUDA_TRY(cudaFuncSetAttribute(k_upsert_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGroupMaxWords) * 7 + int(gsm_pad)));
 			p->grouped_smem_attr = true;
 		}
 		k_upsert_grouped<<<nb, kGroupThreads, gsm, p->stream>>>(
