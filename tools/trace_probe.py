@@ -28,6 +28,9 @@ def main():
     ap.add_argument("--frames", type=int, default=20)
     ap.add_argument("--level", type=int, default=15)
     ap.add_argument("--lod", action="store_true")
+    ap.add_argument("--ab", default="", help="comma list of variant:cta pairs measured round-robin in ONE process, "
+                                             "e.g. 0:128,0:64,0:256,5:128 (HD_TRACE_VARIANT / HD_TRACE_CTA are read per call)")
+    ap.add_argument("--rounds", type=int, default=3)
     a = ap.parse_args()
     bench.LEVEL_COUNT = a.level
     cfg = bench.scene_config()
@@ -38,6 +41,10 @@ def main():
     stream = torch.cuda.ExternalStream(pool.stream, device=0)
     rgba = torch.zeros(W * H, dtype=torch.int32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    if a.ab:
+        ab(a, pool, cfg, root, W, H, stream, rgba, flush)
+        pool.close()
+        return
     out = {}
     for lod in ((False, True) if a.lod else (False,)):
         ev, crc = [], 0
@@ -60,6 +67,38 @@ def main():
                                          "ms_max": round(max(ms), 4), "crc": crc}
     print(json.dumps({"variant": os.environ.get("HD_TRACE_VARIANT", "0"), "level": a.level, **out}))
     pool.close()
+
+
+def ab(a, pool, cfg, root, W, H, stream, rgba, flush):
+    """Round-robin A/B of (variant, CTA size) pairs inside one process: same box, same clocks, same scene."""
+    pairs = [tuple((x.split(":") + ["0"])[:3]) for x in a.ab.split(",")]  # variant : CTA threads [: persistent CTA threads]
+    res = {p: {"full": [], "lod": [], "crc": {}} for p in pairs}
+    with torch.cuda.stream(stream):
+        for rnd in range(a.rounds):
+            for p in pairs:
+                os.environ["HD_TRACE_VARIANT"], os.environ["HD_TRACE_CTA"], os.environ["HD_TRACE_PERSIST"] = p
+                for lod in ((False, True) if a.lod else (False,)):
+                    if lod:  # the LOD default is the hoisted loop: variant 0 -> 4, 5 -> 6
+                        os.environ["HD_TRACE_VARIANT"] = {"0": "4", "5": "6"}.get(p[0], p[0])
+                    ev, crc = [], 0
+                    for s in range(-2, a.frames):
+                        P = bench.camera(cfg, root, s + 1000 * lod, W, H, lod)
+                        flush.fill_(s & 0xFF)
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        pool.TraceDev(P, rgba8=rgba.data_ptr())
+                        e1.record()
+                        if s >= 0:
+                            ev.append((e0, e1))
+                        if s in (0, a.frames - 1):
+                            pool.Sync()
+                            crc = zlib.crc32(rgba.cpu().numpy().tobytes(), crc)
+                    torch.cuda.synchronize()
+                    ms = [x.elapsed_time(y) for x, y in ev]
+                    res[p]["lod" if lod else "full"].append(round(W * H * len(ms) / sum(ms) / 1e3, 1))
+                    res[p]["crc"]["lod" if lod else "full"] = crc
+    for p in pairs:
+        print(json.dumps({"variant": p[0], "cta": p[1], "persist": p[2], **res[p]}))
 
 
 if __name__ == "__main__":

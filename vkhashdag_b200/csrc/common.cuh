@@ -135,6 +135,8 @@ struct hd_pool {
 	uint32_t tt_seen_root = HD_NULL_NODE, tt_seen_frames = 0; // auto mode: build once a root has been traced twice
 	void tt_invalidate() { tt_valid = false, tt_seen_root = HD_NULL_NODE, tt_seen_frames = 0; }
 
+	uint32_t *persist_ctr = nullptr; // chunk counter of the persistent trace kernel (trace.cu: trace_persist_kernel)
+
 	// pipelined frames (hd_trace_submit / hd_trace_collect): two slots, copy stream overlaps the next trace
 	cudaStream_t copy_stream = nullptr;
 	uint32_t *pipe_rgba[2] = {nullptr, nullptr};

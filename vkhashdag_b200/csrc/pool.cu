@@ -217,6 +217,7 @@ void hd_pool_destroy(hd_pool *p) {
 	cudaFree(p->stage_hits);
 	cudaFree(p->params_dev);
 	cudaFree(p->ray_table);
+	cudaFree(p->persist_ctr);
 	cudaFree(p->tt_entries), cudaFree(p->tt_masks), cudaFree(p->tt_list[0]), cudaFree(p->tt_list[1]), cudaFree(p->tt_count);
 	cudaFree(p->dirty_scratch);
 	cudaFreeHost(p->pick_host);
