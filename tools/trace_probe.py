@@ -31,13 +31,26 @@ def main():
     ap.add_argument("--ab", default="", help="comma list of variant:cta pairs measured round-robin in ONE process, "
                                              "e.g. 0:128,0:64,0:256,5:128 (HD_TRACE_VARIANT / HD_TRACE_CTA are read per call)")
     ap.add_argument("--rounds", type=int, default=3)
+    ap.add_argument("--scene", default="cfg2", help="cfg2 (2^15 terrain) or cfg3 (2^17 world, terrain patch + 10 000 sphere edits)")
+    ap.add_argument("--tiled", action="store_true", help="trace through the tile-shard kernels (64x64 tiles, world 1)")
+    ap.add_argument("--size", default="4k", help="4k or 8k frame")
     a = ap.parse_args()
     bench.LEVEL_COUNT = a.level
-    cfg = bench.scene_config()
-    pool = v.DAGNodePool(cfg, device=0)
-    root = pool.Edit(abi.NULL, v.TerrainEditor(cfg.voxel_level))
+    scale = 1.0
+    if a.scene == "cfg3":
+        cfg = bench.cfg3_config()
+        scale = (1 << bench.CFG3_PATCH_BITS) / (1 << cfg.voxel_level)
+        pool = v.DAGNodePool(cfg, device=0)
+        root = pool.Edit(abi.NULL, v.TerrainEditor(cfg.voxel_level, extent_bits=bench.CFG3_PATCH_BITS))
+        root = pool.EditBatch(root, abi.edit_array(abi.random_spheres(bench.EDIT_BATCH, cfg.voxel_level, seed=1234, rmin=16, rmax=256,
+                                                                     extent_bits=bench.CFG3_PATCH_BITS)))
+    else:
+        cfg = bench.scene_config()
+        pool = v.DAGNodePool(cfg, device=0)
+        root = pool.Edit(abi.NULL, v.TerrainEditor(cfg.voxel_level))
     assert pool.last_stats["overflow_count"] == 0
-    W, H = bench.W4K, bench.H4K
+    W, H = (bench.W4K, bench.H4K) if a.size == "4k" else (2 * bench.W4K, 2 * bench.H4K)
+    a.cam_scale, a.shard = scale, ((64, 64, 0, 1) if a.tiled else None)
     stream = torch.cuda.ExternalStream(pool.stream, device=0)
     rgba = torch.zeros(W * H, dtype=torch.int32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -82,11 +95,11 @@ def ab(a, pool, cfg, root, W, H, stream, rgba, flush):
                         os.environ["HD_TRACE_VARIANT"] = {"0": "4", "5": "6"}.get(p[0], p[0])
                     ev, crc = [], 0
                     for s in range(-2, a.frames):
-                        P = bench.camera(cfg, root, s + 1000 * lod, W, H, lod)
+                        P = bench.camera(cfg, root, s + 1000 * lod, W, H, lod, scale=a.cam_scale)
                         flush.fill_(s & 0xFF)
                         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         e0.record()
-                        pool.TraceDev(P, rgba8=rgba.data_ptr())
+                        pool.TraceDev(P, rgba8=rgba.data_ptr(), shard=a.shard)
                         e1.record()
                         if s >= 0:
                             ev.append((e0, e1))
