@@ -192,6 +192,36 @@ def test_lean_frames_equal_the_oracle_on_a_frame_size_change(oracle, hd):
     dev.close()
 
 
+def test_cta_shapes_and_experimental_kernels_are_bit_exact(oracle, hd, monkeypatch):
+    """HD_TRACE_CTA, HD_TRACE_PERSIST and HD_TRACE_VARIANT are read per call: every CTA shape of the grid-per-patch kernel,
+    the persistent chunk-queue kernel and the no-allocate leaf loads must shade exactly the frame the oracle shades, on
+    odd frame sizes (partial patches, partial chunks) with and without LOD; the tile-shard kernels with both CTA shapes."""
+    cfg = abi.default_config(level_count=10, top_level_count=9)
+    opool = oracle.pool(cfg)
+    root = opool.edit_batch(NULL, [abi.terrain(cfg.voxel_level)] + abi.random_spheres(40, cfg.voxel_level, seed=4, rmin=8, rmax=70))
+    dev = hd.DAGNodePool(cfg)
+    dev.UploadFrom(opool)
+    knobs = [{}] + [{"HD_TRACE_CTA": c} for c in ("64", "128", "256", "2560", "512", "1024")] \
+        + [{"HD_TRACE_PERSIST": c} for c in ("256", "512", "1024")] + [{"HD_TRACE_VARIANT": x} for x in ("5", "6")]
+    for (W, H), cam in (((333, 517), ((0.2, 0.7, 0.9), 2.3, -0.3)), ((640, 360), ((0.5, 0.8, 0.5), 0.6, -0.6))):
+        for lod in (False, True):
+            P = abi.camera_params(cfg, root, *cam, W, H, color_root=(1 << 30) | 0x80C040, lod=lod)
+            exp = oracle.trace_frame(opool.words_ptr, P)["rgba8"]
+            for env in knobs:
+                with monkeypatch.context() as m:
+                    for k, val in env.items():
+                        m.setenv(k, val)
+                    got = dev.Trace(P, want=("rgba8",))["rgba8"]
+                assert np.array_equal(got, exp), (W, H, lod, env)
+            shards = []
+            for cta in ("128", "256"):
+                with monkeypatch.context() as m:
+                    m.setenv("HD_TRACE_CTA", cta)
+                    shards.append(dev.Trace(P, want=("rgba8",), shard=(64, 64, 1, 3))["rgba8"])
+            assert np.array_equal(shards[0], shards[1]), (W, H, lod)
+    dev.close()
+
+
 def test_staged_top_levels_equal_the_pool_path(oracle, hd):
     """The staged copy of the top node levels (built once a root is traced for the second time) must not change a single
     output: frames, hit records, iteration counts and F before and after the table exists, across edits (new roots),
