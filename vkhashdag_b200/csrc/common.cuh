@@ -141,6 +141,7 @@ struct hd_pool {
 	cudaStream_t copy_stream = nullptr;
 	uint32_t *pipe_rgba[2] = {nullptr, nullptr};
 	uint64_t pipe_pixels[2] = {0, 0};
+	uint64_t pipe_sig[2][3] = {{0, 0, 0}, {0, 0, 0}}; // frame / shard geometry the slot's padding was last cleared for
 	cudaEvent_t pipe_traced[2] = {nullptr, nullptr}, pipe_done[2] = {nullptr, nullptr};
 	bool pipe_busy[2] = {false, false};
 
