@@ -404,6 +404,8 @@ def run_ours(args):
                 "sector_granular_GBps": round(value * 1e6 * 32.0 * F / 1e9 / n, 1),
                 # lts__t_sectors, l1tex sectors per request, L2 / DRAM GB/s of the same static capture
                 "ncu_memory_system": ncu_static("memory_system"),
+                # the ceiling that binds: warp instructions issued against 148 SMs x 4 schedulers x clock (same static capture)
+                "ncu_issue_roofline": ncu_static("issue_roofline"),
                 "limiter": "instruction issue, not HBM: ncu issue-active / lanes per instruction in profiles/ (static)",
                 "note": "gather-bound: dependent 4-byte loads; the HBM fraction is reported because the contract asks "
                         "for it, the kernel's real ceiling is the SM issue rate (DESIGN.md §3.1)"}
